@@ -1,0 +1,91 @@
+"""Import the UNMODIFIED reference (danielgordon10/vince) on CPU.  TEST INFRASTRUCTURE ONLY.
+
+Only usable in the dev container, where the reference is mounted read-only at
+/root/reference; the GPU box has no such path, so nothing under `tests -m gpu`,
+`bench.py` or `__graft_entry__.smoke()` may call this.  It is used by
+  * oracle/make_golden.py   - to generate tests/golden/*.npz from the real reference
+  * tests/test_oracle_vs_reference.py - to pin oracle/vince_oracle.py to the reference
+    (skipped automatically when /root/reference is absent)
+
+The reference needs two un-installable packages (`dg_util`, `efficientnet_pytorch`);
+oracle/dg_util_shim provides import-level stand-ins.
+"""
+import os
+import sys
+import types
+import warnings
+
+REFERENCE_ROOT = os.environ.get("VINCE_REFERENCE_ROOT", "/root/reference")
+_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dg_util_shim")
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "vince_model.py"))
+
+
+_cached = None
+
+
+def load_reference():
+    """Returns a namespace with the reference's hot-path classes/modules."""
+    global _cached
+    if _cached is not None:
+        return _cached
+    if not reference_available():
+        raise RuntimeError("reference not mounted at %s" % REFERENCE_ROOT)
+    import numpy as np
+
+    if not hasattr(np, "bool"):
+        np.bool = bool  # vince_model.py:54 uses the removed alias
+    for p in (_SHIM, REFERENCE_ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import constants as ref_constants  # noqa: F401  (reference top-level module)
+        from models import vince_model as ref_vince_model
+        from models.building_blocks import backbone_models as ref_backbones
+        from utils import loss_util as ref_loss_util
+        from utils import storage_queue as ref_storage_queue
+    ns = types.SimpleNamespace(
+        VinceModel=ref_vince_model.VinceModel,
+        VinceQueueModel=ref_vince_model.VinceQueueModel,
+        StorageQueue=ref_storage_queue.StorageQueue,
+        loss_util=ref_loss_util,
+        backbones=ref_backbones,
+        vince_model=ref_vince_model,
+    )
+    _cached = ns
+    return ns
+
+
+def make_args(backbone="ResNet18", num_frames=4, batch_size=8, queue_size=1024, embedding_size=128,
+              temperature=0.07, self_temperature=0.03, momentum=0.999, inter_batch_comparison=True,
+              self_batch_comparison=False, jigsaw=False):
+    """argparse.Namespace-alike with the fields the hot path reads."""
+    ref = load_reference()
+    return types.SimpleNamespace(
+        backbone=getattr(ref.backbones, backbone),
+        num_frames=num_frames,
+        use_attention=False,
+        feature_extractor_gpu_ids=["cpu"],
+        pytorch_gpu_ids=["cpu"],
+        vince_embedding_size=embedding_size,
+        vince_queue_size=queue_size,
+        vince_temperature=temperature,
+        vince_self_temperature=self_temperature,
+        vince_momentum=momentum,
+        jigsaw=jigsaw,
+        inter_batch_comparison=inter_batch_comparison,
+        self_batch_comparison=self_batch_comparison,
+        batch_size=batch_size,
+        use_imagenet=False,
+        use_imagenet_weights=False,
+        restore=False,
+        save=False,
+        checkpoint_dir="/tmp/_vince_ref_ckpt",
+        long_save_checkpoint_dir="/tmp/_vince_ref_ckpt_long",
+        long_save_frequency=10,
+        saved_variable_prefix=None,
+        new_variable_prefix=None,
+    )
