@@ -1,0 +1,172 @@
+/* libvince_b200 - C ABI of the B200-native VINCE hot path (encoder forward, fused InfoNCE, EMA + enqueue).
+ *
+ * The reference (danielgordon10/vince) is pure Python on PyTorch and has NO FFI of its own; every entry point
+ * below replaces a PyTorch library call site on its hot path (cited per function, paths relative to the
+ * reference root).  The Python classes in vince_b200/ (VinceModel, VinceQueueModel, StorageQueue,
+ * loss_util.similarity_cross_entropy) bind these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative vince_status; it never throws and never syncs the device;
+ *     vince_last_error() returns a thread-local message for the last failure on the calling thread;
+ *   - all tensor arguments are raw DEVICE pointers owned by the caller, with explicit shapes; nothing is
+ *     allocated inside (scratch comes in through `workspace` arguments sized by *_workspace_bytes());
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - activations between convolutions are NHWC, carried as a pair of bf16 planes (hi, lo) with
+ *     x ~= hi + lo (|err| <= 2^-17 |x|); with `passes` = 3 each MMA k-step computes hi*hi + lo*hi + hi*lo so
+ *     the result matches the reference's fp32 arithmetic to ~1e-5; `passes` = 1 uses the hi plane only
+ *     (plain bf16, lo pointers may be NULL).
+ */
+#ifndef VINCE_B200_H_
+#define VINCE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  VINCE_OK = 0,
+  VINCE_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  VINCE_ERR_CUDA = -2,        /* CUDA runtime or driver error */
+  VINCE_ERR_NCCL = -3,        /* NCCL error, or libnccl could not be loaded */
+  VINCE_ERR_UNSUPPORTED = -4
+} vince_status;
+
+const char* vince_last_error(void);
+int vince_abi_version(void);
+
+/* ---- convolution / linear layer as a tcgen05 implicit GEMM ------------------------------------------------
+ * replaces: torchvision resnet conv2d calls reached from models/building_blocks/backbone_models.py:50-53
+ *           (spec: models/building_blocks/resnet.py:76-92, 117-137, 231-247) and the nn.Linear layers of
+ *           models/vince_model.py:38-49,163,171,177.
+ * out[M,N] (fp32, row-major == NHWC) = epilogue(A * W^T); epilogue = optional per-channel scale, bias, ReLU;
+ * `stats` (optional, [2][N] fp64, accumulated with +=) receives per-channel sum and sum of squares of the raw
+ * outputs for train-mode BatchNorm (resnet.py:79,83 bn1/bn2 in training mode). */
+typedef struct {
+  const void* a_hi;       /* bf16: [M,K] row-major, or NHWC [batch,H,W,Cin] when im2col != 0 */
+  const void* a_lo;
+  const void* w_hi;       /* bf16 [N,K], K ordered (r, s, cin): see vince_weight_prep */
+  const void* w_lo;
+  float* out;
+  int32_t M, N, K;
+  int32_t im2col;
+  int32_t batch, H, W, Cin, R, S, stride, pad_lo_h, pad_lo_w, pad_hi_h, pad_hi_w;
+  int32_t passes;         /* 3 or 1 */
+  int32_t block_n;        /* 0 = auto; 64 / 128 / 256 */
+  const float* scale;
+  const float* bias;
+  int32_t relu;
+  int32_t reserved;
+  double* stats;
+} vince_conv_desc;
+int vince_conv_fwd(const vince_conv_desc* desc, void* stream);
+
+/* ---- stem input packing: NCHW fp32 -> X[n, j, q, 64] bf16 (hi, lo) ------------------------------------------
+ * replaces: the input side of conv1 (7x7/2, pad 3; resnet.py:170,233) and the shuffle gather data[shuffle_order]
+ *           (vince_model.py:142) when gather_idx != NULL.
+ * X[n,j,q, r2*21+s*3+c] = x[gather_idx[n], c, 2j-1+r2, 2q-3+s]; Hj = H/2+1, Q = (W-1)/2+1.  The stem then runs as
+ * vince_conv_fwd with batch,H,W,Cin = N,Hj,Q,64, R=4,S=1, stride 1, pad_lo_h=1, pad_hi_h = P+2-Hj. */
+int vince_stem_pack(const float* x, const int64_t* gather_idx, void* x_hi, void* x_lo, int32_t N, int32_t H, int32_t W,
+                    void* stream);
+
+/* ---- weight preparation (multi-tensor): OIHW fp32 -> K-major bf16 (hi, lo) ----------------------------------
+ * replaces: nothing in the reference (cuDNN consumes OIHW directly); run after every weight update. */
+typedef struct {
+  const float* src;       /* [Cout,Cin,R,S] fp32 */
+  int64_t dst_off;        /* element offset into w_hi / w_lo */
+  int32_t Cout, Cin, R, S;
+  int32_t kind;           /* 0: [Cout][R][S][Cin];  1: packed 7x7 stem -> [64][4][64] */
+  int32_t pad;
+} vince_weight_entry;
+int vince_weight_prep(const vince_weight_entry* table_dev, int32_t n_entries, int64_t max_elems, void* w_hi, void* w_lo,
+                      void* stream);
+
+/* ---- BatchNorm apply (+residual, +ReLU) and pooling ----------------------------------------------------------
+ * replaces: nn.BatchNorm2d forward (train: batch statistics + running-stat update, momentum 0.1, unbiased var;
+ *           eval: running statistics), the residual add and ReLU of resnet.py:76-92 / 117-137, MaxPool2d
+ *           (resnet.py:173,236) and AdaptiveAvgPool2d (vince_model.py:33,128).
+ * A `vince_bn_side` with stats == NULL means eval mode (running statistics, no update). */
+typedef struct {
+  const float* raw;       /* [M,C] raw conv output (NHWC) */
+  const double* stats;    /* [2][C] from vince_conv_fwd, or NULL */
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  int64_t* num_batches_tracked;
+} vince_bn_side;
+/* out = relu?( bn(main) + residual ); res_kind 0 none, 1 (res_hi,res_lo) planes, 2 bn(res_bn) (downsample branch) */
+int vince_bn_apply(const vince_bn_side* main, int32_t res_kind, const void* res_hi, const void* res_lo,
+                   const vince_bn_side* res_bn, int32_t relu, void* out_hi, void* out_lo, float* out_f32, int64_t M,
+                   int32_t C, float momentum, float eps, void* stream);
+int vince_bn_relu_maxpool(const vince_bn_side* bn, void* out_hi, void* out_lo, int32_t N, int32_t P, int32_t Q, int32_t C,
+                          float momentum, float eps, void* stream);
+/* last block: relu(bn(main)+residual) -> spatial_features NCHW fp32 [N,C,h,w] + extracted_features [N,C]; output
+ * row n is written at scatter_idx[n] (the un-shuffle of vince_model.py:184-192) */
+int vince_bn_final_pool(const vince_bn_side* main, int32_t res_kind, const void* res_hi, const void* res_lo,
+                        const vince_bn_side* res_bn, const int64_t* scatter_idx, float* spatial_nchw, float* pooled,
+                        int32_t N, int32_t HW, int32_t C, float momentum, float eps, void* stream);
+
+/* ---- small helpers --------------------------------------------------------------------------------------------
+ * vince_l2_normalize replaces F.normalize(dim=1) (vince_model.py:180); the jigsaw pair replaces
+ * vince_model.py:144-155 and :164-170. */
+int vince_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream);
+int vince_round_tf32(const float* x, float* out, int64_t n, void* stream);
+int vince_l2_normalize(const float* x, float* out, int32_t rows, int32_t D, float eps, void* stream);
+int vince_jigsaw_patchify(const float* x, const int64_t* gather_idx, float* out, int32_t N, int32_t C, int32_t H,
+                          int32_t W, void* stream);
+int vince_jigsaw_gather(const float* in, const int64_t* order, float* out, int32_t N, int32_t C, void* stream);
+
+/* ---- fused InfoNCE forward ----------------------------------------------------------------------------------
+ * replaces: VinceModel.forward similarity matmuls (vince_model.py:213-233), loss_util.similarity_cross_entropy
+ *           (utils/loss_util.py:7-62) and the metric passes of VinceModel.get_metrics (vince_model.py:314-342). */
+typedef struct {
+  const float* q;
+  const float* keys;
+  const float* queue_tf32;
+  int32_t B, Bk, K, D;
+  int32_t num_frames;     /* >0: inter-batch comparison, block-diagonal positives; 0: MoCo (l_pos = q_i . k_i) */
+  float temperature;
+  float* dists;
+  float* weights;
+  float* pos_sim;
+  float* neg_max;
+  float* row_lse;
+  float* scalars;         /* [8]: 0 dist, 1 softmax_weight, 2 nce_accuracy, 3 cosine_sim, 4 cosine_sim_neg_max */
+  void* workspace;
+} vince_infonce_desc;
+size_t vince_infonce_workspace_bytes(int32_t B, int32_t D);
+int vince_infonce_fwd(const vince_infonce_desc* desc, void* stream);
+
+/* ---- fused momentum EMA (multi-tensor) + ring-buffer enqueue ----------------------------------------------------
+ * replaces: VinceQueueModel.param_update (vince_model.py:587-592; ~2 launches per parameter tensor) and the
+ *           copy_ calls of StorageQueue.enqueue (utils/storage_queue.py:38,46).
+ * The table holds one entry per <= 8192 contiguous floats of one parameter tensor.  The enqueue part copies
+ * keys[0:n0] to queue[dst0:...] and keys[src1:src1+n1] to queue[dst1:...] (element offsets; n1 > 0 on wrap-around);
+ * when queue_tf32 != NULL the TF32-rounded shadow used by vince_infonce_fwd is written in the same pass. */
+typedef struct {
+  float* dst;
+  const float* src;
+  int64_t count;
+} vince_ema_chunk;
+int vince_ema_enqueue(const vince_ema_chunk* table_dev, int32_t n_chunks, float momentum, float one_minus_momentum,
+                      float* queue, float* queue_tf32, const float* keys, int64_t n0, int64_t dst0, int64_t n1,
+                      int64_t dst1, int64_t src1, void* stream);
+
+/* ---- multi-GPU: NCCL all-gather of the keys straight into the ring buffer -------------------------------------
+ * replaces: the implicit nn.DataParallel gather of vince_model.py:35,125 + StorageQueue.enqueue; one process per
+ * GPU.  `unique_id` is the 128-byte ncclUniqueId produced by vince_comm_unique_id on rank 0 and broadcast by the
+ * host program.  vince_allgather_enqueue gathers keys[n_local, D] of every rank, in rank order, into
+ * queue rows [tail, tail + world*n_local) mod K (and the TF32 shadow), using `scratch` (world*n_local*D floats). */
+int vince_comm_unique_id(void* unique_id_128);
+int vince_comm_init(void** comm_out, const void* unique_id_128, int32_t world, int32_t rank);
+int vince_comm_destroy(void* comm);
+int vince_allgather_enqueue(void* comm, const float* keys, int64_t n_local, int32_t D, float* queue, float* queue_tf32,
+                            int64_t K, int64_t tail, float* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VINCE_B200_H_ */

@@ -1,0 +1,98 @@
+"""ctypes binding of libvince_b200.so (the C ABI declared in include/vince_b200.h).
+
+There is no CPU or PyTorch fallback: if the library cannot be loaded `lib()` raises, and every op in
+vince_b200.ops refuses non-CUDA tensors.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libvince_b200.so")
+
+
+class ConvDesc(Structure):
+    _fields_ = [
+        ("a_hi", c_void_p), ("a_lo", c_void_p), ("w_hi", c_void_p), ("w_lo", c_void_p), ("out", c_void_p),
+        ("M", c_int32), ("N", c_int32), ("K", c_int32), ("im2col", c_int32),
+        ("batch", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("R", c_int32), ("S", c_int32),
+        ("stride", c_int32), ("pad_lo_h", c_int32), ("pad_lo_w", c_int32), ("pad_hi_h", c_int32),
+        ("pad_hi_w", c_int32), ("passes", c_int32), ("block_n", c_int32),
+        ("scale", c_void_p), ("bias", c_void_p), ("relu", c_int32), ("reserved", c_int32), ("stats", c_void_p),
+    ]
+
+
+class BnSide(Structure):
+    _fields_ = [
+        ("raw", c_void_p), ("stats", c_void_p), ("gamma", c_void_p), ("beta", c_void_p),
+        ("running_mean", c_void_p), ("running_var", c_void_p), ("num_batches_tracked", c_void_p),
+    ]
+
+
+class InfoNceDesc(Structure):
+    _fields_ = [
+        ("q", c_void_p), ("keys", c_void_p), ("queue_tf32", c_void_p),
+        ("B", c_int32), ("Bk", c_int32), ("K", c_int32), ("D", c_int32), ("num_frames", c_int32),
+        ("temperature", c_float),
+        ("dists", c_void_p), ("weights", c_void_p), ("pos_sim", c_void_p), ("neg_max", c_void_p),
+        ("row_lse", c_void_p), ("scalars", c_void_p), ("workspace", c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); mirrors include/vince_b200.h one to one
+SIGNATURES = {
+    "vince_last_error": (c_char_p, []),
+    "vince_abi_version": (c_int32, []),
+    "vince_conv_fwd": (c_int32, [POINTER(ConvDesc), c_void_p]),
+    "vince_stem_pack": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "vince_weight_prep": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
+    "vince_bn_apply": (c_int32, [POINTER(BnSide), c_int32, c_void_p, c_void_p, POINTER(BnSide), c_int32, c_void_p,
+                                 c_void_p, c_void_p, c_int64, c_int32, c_float, c_float, c_void_p]),
+    "vince_bn_relu_maxpool": (c_int32, [POINTER(BnSide), c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                        c_float, c_float, c_void_p]),
+    "vince_bn_final_pool": (c_int32, [POINTER(BnSide), c_int32, c_void_p, c_void_p, POINTER(BnSide), c_void_p,
+                                      c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_void_p]),
+    "vince_split_bf16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "vince_round_tf32": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "vince_l2_normalize": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),
+    "vince_jigsaw_patchify": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "vince_jigsaw_gather": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "vince_infonce_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "vince_infonce_fwd": (c_int32, [POINTER(InfoNceDesc), c_void_p]),
+    "vince_ema_enqueue": (c_int32, [c_void_p, c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int64,
+                                    c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "vince_comm_unique_id": (c_int32, [c_void_p]),
+    "vince_comm_init": (c_int32, [POINTER(c_void_p), c_void_p, c_int32, c_int32]),
+    "vince_comm_destroy": (c_int32, [c_void_p]),
+    "vince_allgather_enqueue": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_int64,
+                                          c_void_p, c_void_p]),
+}
+
+_dll = None
+
+
+def lib():
+    """The loaded shared library; raises (never falls back) if it is missing."""
+    global _dll
+    if _dll is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libvince_b200.so is not built (%s). Run `python -m vince_b200.build`; there is no CPU / PyTorch "
+                "fallback for the vince_b200 hot path." % LIB_PATH)
+        dll = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(dll, name)
+            fn.restype = res
+            fn.argtypes = args
+        _dll = dll
+    return _dll
+
+
+def last_error():
+    msg = lib().vince_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (status %d): %s" % (what, rc, last_error()))

@@ -1,0 +1,258 @@
+// extern "C" surface of libvince_b200 (see include/vince_b200.h).  Thin: validates, converts the POD structs to
+// the internal descriptors, launches.  NCCL is bound at run time with dlopen so the library loads (and exports
+// every symbol) on machines without NCCL or a GPU.
+#include <dlfcn.h>
+
+#include "../../include/vince_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace vb;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline __nv_bfloat16* BF(void* p) { return reinterpret_cast<__nv_bfloat16*>(p); }
+static inline const __nv_bfloat16* BF(const void* p) { return reinterpret_cast<const __nv_bfloat16*>(p); }
+
+static BnSide to_side(const vince_bn_side* s) {
+  BnSide o;
+  memset(&o, 0, sizeof(o));
+  if (s) {
+    o.raw = s->raw, o.stats = s->stats, o.gamma = s->gamma, o.beta = s->beta;
+    o.running_mean = s->running_mean, o.running_var = s->running_var, o.num_batches_tracked = s->num_batches_tracked;
+  }
+  return o;
+}
+
+static int check_side(const vince_bn_side* s, const char* what) {
+  VB_REQUIRE(s != nullptr, "%s: null bn side", what);
+  VB_REQUIRE(s->raw && s->gamma && s->beta && s->running_mean && s->running_var, "%s: null pointer in bn side", what);
+  return VB_OK;
+}
+
+extern "C" {
+
+const char* vince_last_error(void) { return get_error(); }
+int vince_abi_version(void) { return 1; }
+
+int vince_conv_fwd(const vince_conv_desc* d, void* stream) {
+  VB_REQUIRE(d != nullptr, "vince_conv_fwd: null descriptor");
+  ConvGemmDesc g;
+  memset(&g, 0, sizeof(g));
+  g.a_hi = d->a_hi, g.a_lo = d->a_lo, g.b_hi = d->w_hi, g.b_lo = d->w_lo, g.out = d->out;
+  g.M = d->M, g.N = d->N, g.K = d->K, g.im2col = d->im2col;
+  g.batch = d->batch, g.H = d->H, g.W = d->W, g.Cin = d->Cin, g.R = d->R, g.S = d->S, g.stride = d->stride;
+  g.pad_lo_h = d->pad_lo_h, g.pad_lo_w = d->pad_lo_w, g.pad_hi_h = d->pad_hi_h, g.pad_hi_w = d->pad_hi_w;
+  g.passes = d->passes, g.block_n = d->block_n, g.scale = d->scale, g.bias = d->bias, g.relu = d->relu;
+  g.stats = d->stats;
+  return conv_gemm_launch(g, S(stream));
+}
+
+int vince_stem_pack(const float* x, const int64_t* gather_idx, void* x_hi, void* x_lo, int32_t N, int32_t H, int32_t W,
+                    void* stream) {
+  VB_REQUIRE(x && x_hi, "vince_stem_pack: null pointer");
+  VB_REQUIRE(N >= 0 && H > 0 && W > 0, "vince_stem_pack: bad shape N=%d H=%d W=%d", N, H, W);
+  return stem_pack_launch(x, gather_idx, BF(x_hi), BF(x_lo), N, H, W, H / 2 + 1, (W - 1) / 2 + 1, S(stream));
+}
+
+int vince_weight_prep(const vince_weight_entry* table_dev, int32_t n_entries, int64_t max_elems, void* w_hi, void* w_lo,
+                      void* stream) {
+  static_assert(sizeof(vince_weight_entry) == sizeof(WeightPrepEntry), "ABI struct mismatch");
+  VB_REQUIRE(n_entries == 0 || (table_dev && w_hi), "vince_weight_prep: null pointer");
+  return weight_prep_launch(reinterpret_cast<const WeightPrepEntry*>(table_dev), n_entries, max_elems, BF(w_hi),
+                            BF(w_lo), S(stream));
+}
+
+int vince_bn_apply(const vince_bn_side* main, int32_t res_kind, const void* res_hi, const void* res_lo,
+                   const vince_bn_side* res_bn, int32_t relu, void* out_hi, void* out_lo, float* out_f32, int64_t M,
+                   int32_t C, float momentum, float eps, void* stream) {
+  int rc = check_side(main, "vince_bn_apply");
+  if (rc) return rc;
+  VB_REQUIRE(res_kind >= 0 && res_kind <= 2, "vince_bn_apply: res_kind %d", res_kind);
+  VB_REQUIRE(res_kind != 1 || res_hi, "vince_bn_apply: residual planes null");
+  if (res_kind == 2 && (rc = check_side(res_bn, "vince_bn_apply(residual)"))) return rc;
+  VB_REQUIRE(out_hi || out_f32, "vince_bn_apply: no output");
+  return bn_apply_launch(to_side(main), res_kind, BF(res_hi), BF(res_lo), to_side(res_bn), relu, BF(out_hi), BF(out_lo),
+                         out_f32, M, C, momentum, eps, S(stream));
+}
+
+int vince_bn_relu_maxpool(const vince_bn_side* bn, void* out_hi, void* out_lo, int32_t N, int32_t P, int32_t Q, int32_t C,
+                          float momentum, float eps, void* stream) {
+  int rc = check_side(bn, "vince_bn_relu_maxpool");
+  if (rc) return rc;
+  VB_REQUIRE(out_hi, "vince_bn_relu_maxpool: null output");
+  const int P2 = (P + 2 - 3) / 2 + 1, Q2 = (Q + 2 - 3) / 2 + 1;
+  return bn_relu_maxpool_launch(to_side(bn), BF(out_hi), BF(out_lo), N, P, Q, C, P2, Q2, momentum, eps, S(stream));
+}
+
+int vince_bn_final_pool(const vince_bn_side* main, int32_t res_kind, const void* res_hi, const void* res_lo,
+                        const vince_bn_side* res_bn, const int64_t* scatter_idx, float* spatial_nchw, float* pooled,
+                        int32_t N, int32_t HW, int32_t C, float momentum, float eps, void* stream) {
+  int rc = check_side(main, "vince_bn_final_pool");
+  if (rc) return rc;
+  VB_REQUIRE(res_kind >= 0 && res_kind <= 2, "vince_bn_final_pool: res_kind %d", res_kind);
+  VB_REQUIRE(res_kind != 1 || res_hi, "vince_bn_final_pool: residual planes null");
+  if (res_kind == 2 && (rc = check_side(res_bn, "vince_bn_final_pool(residual)"))) return rc;
+  VB_REQUIRE(pooled, "vince_bn_final_pool: pooled output null");
+  return bn_final_pool_launch(to_side(main), res_kind, BF(res_hi), BF(res_lo), to_side(res_bn), scatter_idx,
+                              spatial_nchw, pooled, N, HW, C, momentum, eps, S(stream));
+}
+
+int vince_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
+  VB_REQUIRE(n == 0 || (x && hi), "vince_split_bf16: null pointer");
+  return split_bf16_launch(x, BF(hi), BF(lo), n, S(stream));
+}
+int vince_round_tf32(const float* x, float* out, int64_t n, void* stream) {
+  VB_REQUIRE(n == 0 || (x && out), "vince_round_tf32: null pointer");
+  return round_tf32_launch(x, out, n, S(stream));
+}
+int vince_l2_normalize(const float* x, float* out, int32_t rows, int32_t D, float eps, void* stream) {
+  VB_REQUIRE(rows == 0 || (x && out), "vince_l2_normalize: null pointer");
+  return l2_normalize_launch(x, out, rows, D, eps, S(stream));
+}
+int vince_jigsaw_patchify(const float* x, const int64_t* gather_idx, float* out, int32_t N, int32_t C, int32_t H,
+                          int32_t W, void* stream) {
+  VB_REQUIRE(N == 0 || (x && out), "vince_jigsaw_patchify: null pointer");
+  const int Hp = (H % 3) ? H + 3 - H % 3 : H, Wp = (W % 3) ? W + 3 - W % 3 : W;
+  return jigsaw_patchify_launch(x, gather_idx, out, N, C, H, W, Hp / 3, Wp / 3, S(stream));
+}
+int vince_jigsaw_gather(const float* in, const int64_t* order, float* out, int32_t N, int32_t C, void* stream) {
+  VB_REQUIRE(N == 0 || (in && order && out), "vince_jigsaw_gather: null pointer");
+  return jigsaw_gather_launch(in, order, out, N, C, S(stream));
+}
+
+size_t vince_infonce_workspace_bytes(int32_t B, int32_t D) { return infonce_workspace_bytes(B, D); }
+
+int vince_infonce_fwd(const vince_infonce_desc* d, void* stream) {
+  VB_REQUIRE(d != nullptr, "vince_infonce_fwd: null descriptor");
+  VB_REQUIRE(d->dists && d->weights && d->pos_sim && d->neg_max && d->row_lse && d->scalars,
+             "vince_infonce_fwd: null output pointer");
+  InfoNceDesc n;
+  memset(&n, 0, sizeof(n));
+  n.q = d->q, n.keys = d->keys, n.queue_tf32 = d->queue_tf32;
+  n.B = d->B, n.Bk = d->Bk, n.K = d->K, n.D = d->D, n.num_frames = d->num_frames, n.temperature = d->temperature;
+  n.dists = d->dists, n.weights = d->weights, n.pos_sim = d->pos_sim, n.neg_max = d->neg_max, n.row_lse = d->row_lse;
+  n.scalars = d->scalars, n.workspace = d->workspace;
+  return infonce_fwd_launch(n, S(stream));
+}
+
+int vince_ema_enqueue(const vince_ema_chunk* table_dev, int32_t n_chunks, float momentum, float one_minus_momentum,
+                      float* queue, float* queue_tf32, const float* keys, int64_t n0, int64_t dst0, int64_t n1,
+                      int64_t dst1, int64_t src1, void* stream) {
+  static_assert(sizeof(vince_ema_chunk) == sizeof(EmaChunk), "ABI struct mismatch");
+  VB_REQUIRE(n_chunks == 0 || table_dev, "vince_ema_enqueue: null table");
+  VB_REQUIRE((n0 + n1 == 0) || (queue && keys), "vince_ema_enqueue: null queue / keys");
+  VB_REQUIRE(n0 >= 0 && n1 >= 0, "vince_ema_enqueue: negative count");
+  return ema_enqueue_launch(reinterpret_cast<const EmaChunk*>(table_dev), n_chunks, momentum, one_minus_momentum, queue,
+                            queue_tf32, keys, n0, dst0, n1, dst1, src1, S(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// NCCL (bound lazily)
+// ---------------------------------------------------------------------------------------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct {
+  char internal[128];
+} ncclUniqueId;
+typedef int ncclResult_t;
+static struct {
+  void* handle;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int /*dtype*/, ncclComm_t, cudaStream_t);
+  const char* (*GetErrorString)(ncclResult_t);
+} g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.handle) return VB_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD);   // prefer the instance torch already loaded
+    if (!h) h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) {
+    set_error("libnccl.so.2 could not be loaded: %s", dlerror());
+    return VB_ERR_NCCL;
+  }
+  g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+  g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+  g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+  g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(dlsym(h, "ncclAllGather"));
+  g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather) {
+    set_error("libnccl is missing required symbols");
+    return VB_ERR_NCCL;
+  }
+  g_nccl.handle = h;
+  return VB_OK;
+}
+
+#define VB_CHECK_NCCL(expr)                                                                              \
+  do {                                                                                                   \
+    ncclResult_t _r = (expr);                                                                            \
+    if (_r != 0) {                                                                                       \
+      set_error("NCCL error %d (%s) at %s", (int)_r, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?", #expr); \
+      return VB_ERR_NCCL;                                                                                \
+    }                                                                                                    \
+  } while (0)
+
+int vince_comm_unique_id(void* unique_id_128) {
+  VB_REQUIRE(unique_id_128, "vince_comm_unique_id: null buffer");
+  int rc = load_nccl();
+  if (rc) return rc;
+  VB_CHECK_NCCL(g_nccl.GetUniqueId(reinterpret_cast<ncclUniqueId*>(unique_id_128)));
+  return VB_OK;
+}
+
+int vince_comm_init(void** comm_out, const void* unique_id_128, int32_t world, int32_t rank) {
+  VB_REQUIRE(comm_out && unique_id_128, "vince_comm_init: null pointer");
+  VB_REQUIRE(world >= 1 && rank >= 0 && rank < world, "vince_comm_init: bad rank %d / world %d", rank, world);
+  int rc = load_nccl();
+  if (rc) return rc;
+  ncclUniqueId id;
+  memcpy(&id, unique_id_128, sizeof(id));
+  ncclComm_t comm = nullptr;
+  VB_CHECK_NCCL(g_nccl.CommInitRank(&comm, world, id, rank));
+  *comm_out = comm;
+  return VB_OK;
+}
+
+int vince_comm_destroy(void* comm) {
+  if (!comm) return VB_OK;
+  int rc = load_nccl();
+  if (rc) return rc;
+  VB_CHECK_NCCL(g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(comm)));
+  return VB_OK;
+}
+
+int vince_allgather_enqueue(void* comm, const float* keys, int64_t n_local, int32_t D, float* queue, float* queue_tf32,
+                            int64_t K, int64_t tail, float* scratch, void* stream) {
+  VB_REQUIRE(comm && keys && queue && scratch, "vince_allgather_enqueue: null pointer");
+  VB_REQUIRE(D > 0 && D % 4 == 0, "vince_allgather_enqueue: D=%d must be a positive multiple of 4", D);
+  VB_REQUIRE(K > 0 && tail >= 0 && tail <= K, "vince_allgather_enqueue: bad tail %lld for K=%lld", (long long)tail,
+             (long long)K);
+  int rc = load_nccl();
+  if (rc) return rc;
+  int world = 0;
+  {
+    typedef ncclResult_t (*CountFn)(ncclComm_t, int*);
+    CountFn count = reinterpret_cast<CountFn>(dlsym(g_nccl.handle, "ncclCommCount"));
+    VB_REQUIRE(count, "libnccl lacks ncclCommCount");
+    VB_CHECK_NCCL(count(reinterpret_cast<ncclComm_t>(comm), &world));
+  }
+  const int64_t total_rows = n_local * world;
+  VB_REQUIRE(total_rows <= K, "vince_allgather_enqueue: gathered batch (%lld rows) exceeds the queue (%lld)",
+             (long long)total_rows, (long long)K);
+  // rank-ordered gather (ncclFloat32 == 7), then one kernel scatters into the ring (two slices on wrap-around)
+  VB_CHECK_NCCL(g_nccl.AllGather(keys, scratch, (size_t)(n_local * D), 7, reinterpret_cast<ncclComm_t>(comm), S(stream)));
+  int64_t t = tail;
+  if (t + total_rows > K && t == K) t = 0;   // storage_queue.py:35-43 with an empty head slice
+  const int64_t first = (t + total_rows > K) ? (K - t) : total_rows;
+  const int64_t second = total_rows - first;
+  return ema_enqueue_launch(nullptr, 0, 0.f, 1.f, queue, queue_tf32, scratch, first * D, t * D, second * D, 0,
+                            first * D, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,413 @@
+// Fused InfoNCE forward for sm_100a (replaces vince_model.py:198-250 cat+mm, loss_util.py:7-62 and the
+// metric passes of vince_model.py:314-342): the [B, Bk+K] similarity matrix is never written.
+//
+//   main kernel   : persistent, warp-specialised.  Each CTA owns one 128-row block of queries (resident in
+//                   shared memory) and a contiguous range of 128-column tiles of [keys || queue]; tiles are
+//                   streamed by TMA, multiplied on the tensor cores (tcgen05 kind::tf32, fp32 accumulate in
+//                   double-buffered TMEM) and consumed straight from TMEM by 128 epilogue threads (one query
+//                   row each) that keep an online (max, sum-exp) over the NEGATIVE columns.
+//   finalize      : one block; merges the per-CTA partials, evaluates the positives with exact fp32 dot
+//                   products, and emits the per-positive losses/weights, the saved row statistics and the
+//                   five scalars the reference computes every step (loss, softmax weight, accuracy, cosine_sim,
+//                   cosine_sim_neg_max) with a fixed (deterministic) reduction order.
+//
+// Operands are fp32 values pre-rounded (round-to-nearest) to TF32 so that the tensor core's truncation of
+// the low 13 mantissa bits is exact: queries/keys are rounded by a tiny pre-pass into the workspace, the
+// queue by its owner at enqueue time (`queue_tf32`, see StorageQueue); positives use the un-rounded data.
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vb {
+
+constexpr int NCE_BM = 128;
+constexpr int NCE_BN = 128;
+constexpr int NCE_THREADS = 192;
+constexpr int NCE_MAX_STAGES = 4;
+
+struct NceParams {
+  CUtensorMap q_map, keys_map, queue_map;
+  int B, Bk, K, D;
+  int nf;
+  int nmb, nkt, nqt, slices;
+  int num_stages;
+  float scale_log2;
+  float2* partials;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(NCE_THREADS, 1) infonce_main_kernel(const __grid_constant__ NceParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int atoms = p.D / 32;                          // 128-byte swizzle atoms along D
+  const uint32_t q_bytes = atoms * NCE_BM * 128;
+  const uint32_t stage_bytes = atoms * NCE_BN * 128;
+
+  uint8_t* q_smem = smem;
+  uint8_t* stages = smem + q_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stages + (size_t)p.num_stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + NCE_MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + NCE_MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* q_full = tmem_empty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(q_full + 1);
+
+  const int m_blk = blockIdx.x % p.nmb;
+  const int sidx = blockIdx.x / p.nmb;
+  const int T = p.nkt + p.nqt;
+  const int t_begin = (int)(((int64_t)T * sidx) / p.slices);
+  const int t_end = (int)(((int64_t)T * (sidx + 1)) / p.slices);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.q_map);
+    if (p.nkt) tma_prefetch_desc(&p.keys_map);
+    if (p.nqt) tma_prefetch_desc(&p.queue_map);
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 128);
+    }
+    mbar_init(q_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 2 * NCE_BN);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0 && t_end > t_begin) {
+      mbar_expect_tx(q_full, q_bytes);
+      for (int a = 0; a < atoms; ++a) tma_load_2d(q_smem + a * NCE_BM * 128, &p.q_map, q_full, a * 32, m_blk * NCE_BM);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = stages + (size_t)stage * stage_bytes;
+        mbar_expect_tx(&full_bar[stage], stage_bytes);
+        const bool is_key = t < p.nkt;
+        const CUtensorMap* map = is_key ? &p.keys_map : &p.queue_map;
+        const int row0 = (is_key ? t : t - p.nkt) * NCE_BN;
+        for (int a = 0; a < atoms; ++a) tma_load_2d(st + a * NCE_BN * 128, map, &full_bar[stage], a * 32, row0);
+        if (++stage == p.num_stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && t_end > t_begin) {
+      constexpr uint32_t idesc = make_idesc(UMMA_FMT_TF32, NCE_BM, NCE_BN);
+      mbar_wait(q_full, 0);
+      tc_fence_after_sync();
+      const uint32_t q_addr = smem_u32(q_smem);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t_begin, lt = 0; t < t_end; ++t, ++lt) {
+        const int acc = lt & 1;
+        const uint32_t acc_phase = (lt >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after_sync();
+        const uint32_t st = smem_u32(stages + (size_t)stage * stage_bytes);
+        const uint32_t d_tmem = tmem_base + acc * NCE_BN;
+        for (int a = 0; a < atoms; ++a) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {          // 8 tf32 (32 bytes) per MMA
+            const uint64_t da = make_smem_desc(q_addr + a * NCE_BM * 128 + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t db = make_smem_desc(st + a * NCE_BN * 128 + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
+            umma_tf32(d_tmem, da, db, idesc, (a | k) != 0);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&tmem_full[acc]);
+        if (++stage == p.num_stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- online softmax over negatives, one query row per thread ----
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int i = m_blk * NCE_BM + r;                 // global query row
+    const int pos_lo = p.nf > 0 ? (i / p.nf) * p.nf : -1;
+    const int pos_hi = p.nf > 0 ? pos_lo + p.nf : -1;
+    float nmax = -INFINITY;                           // running max of raw similarities over negatives
+    float Z = 0.f;                                    // sum exp2((sigma - nmax) * scale_log2) over negatives
+    const float c = p.scale_log2;
+    for (int t = t_begin, lt = 0; t < t_end; ++t, ++lt) {
+      const int acc = lt & 1;
+      const uint32_t acc_phase = (lt >> 1) & 1;
+      const bool is_key = t < p.nkt;
+      const int j0 = (is_key ? t : t - p.nkt) * NCE_BN;
+      const int limit = is_key ? p.Bk : p.K;
+      const bool needs_mask = is_key || (j0 + NCE_BN > limit);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int chunk = 0; chunk < NCE_BN / 32; ++chunk) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * NCE_BN + chunk * 32, raw);
+        tmem_ld_wait();
+        if (chunk == NCE_BN / 32 - 1) {
+          tc_fence_before_sync();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+        float v[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]);
+        if (needs_mask) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int j = j0 + chunk * 32 + e;
+            const bool is_pos = is_key && j >= pos_lo && j < pos_hi;
+            if (j >= limit || is_pos) v[e] = -INFINITY;
+          }
+        }
+        float cm = v[0];
+#pragma unroll
+        for (int e = 1; e < 32; ++e) cm = fmaxf(cm, v[e]);
+        if (cm > nmax) {
+          Z *= fast_exp2((nmax - cm) * c);            // nmax = -inf on first use: Z is 0, exp2(-inf) = 0
+          nmax = cm;
+        }
+        const float off = (nmax == -INFINITY) ? 0.f : -nmax * c;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          s0 += fast_exp2(fmaf(v[e], c, off));
+          s1 += fast_exp2(fmaf(v[e + 1], c, off));
+        }
+        Z += s0 + s1;
+      }
+    }
+    p.partials[((size_t)m_blk * p.slices + sidx) * NCE_BM + r] = make_float2(nmax, Z);
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 2 * NCE_BN);
+  }
+}
+
+// round-to-nearest fp32 -> tf32 (kept in an fp32 container)
+__global__ void round_tf32_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x[i]));
+    out[i] = __uint_as_float(u);
+  }
+}
+
+int round_tf32_launch(const float* x, float* out, int64_t n, cudaStream_t stream) {
+  if (n == 0) return VB_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  round_tf32_kernel<<<(int)blocks, 256, 0, stream>>>(x, out, n);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB_OK;
+}
+
+struct NceFinalizeParams {
+  const float* q;
+  const float* keys;
+  const float2* partials;
+  int B, D, nf, nP, nmb, slices;
+  float temperature, scale_log2;
+  float* dists;
+  float* weights;
+  float* pos_sim;
+  float* neg_max;
+  float* row_lse;
+  float* scalars;
+};
+
+__global__ void __launch_bounds__(1024, 1) infonce_finalize_kernel(const NceFinalizeParams p) {
+  __shared__ float red[5][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  // per-warp running sums, accumulated in a fixed row order -> deterministic
+  float sum_dist = 0.f, sum_w = 0.f, sum_acc = 0.f, sum_pos = 0.f, sum_negmax = 0.f;
+  for (int i = warp; i < p.B; i += nwarps) {
+    const int m_blk = i / NCE_BM, r = i % NCE_BM;
+    // merge partials over slices (lanes stride over slices)
+    float nmax = -INFINITY;
+    for (int s = lane; s < p.slices; s += 32)
+      nmax = fmaxf(nmax, p.partials[((size_t)m_blk * p.slices + s) * NCE_BM + r].x);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nmax = fmaxf(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+    float Z = 0.f;
+    for (int s = lane; s < p.slices; s += 32) {
+      const float2 pr = p.partials[((size_t)m_blk * p.slices + s) * NCE_BM + r];
+      if (pr.x != -INFINITY) Z += pr.y * exp2f((pr.x - nmax) * p.scale_log2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(0xffffffffu, Z, o);
+    // positives: exact fp32 dot products
+    const int pos0 = p.nf > 0 ? (i / p.nf) * p.nf : i;
+    float zmax = (nmax == -INFINITY) ? -INFINITY : nmax / p.temperature;
+    float sig[8];
+    for (int pp = 0; pp < p.nP; ++pp) {
+      const float* kr = p.keys + (size_t)(pos0 + pp) * p.D;
+      const float* qr = p.q + (size_t)i * p.D;
+      float d = 0.f;
+      for (int e = lane; e < p.D; e += 32) d = fmaf(qr[e], kr[e], d);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      sig[pp] = d;
+      zmax = fmaxf(zmax, d / p.temperature);
+    }
+    // Zneg relative to the row max over ALL columns (loss_util.py:24)
+    const float Zn = (nmax == -INFINITY) ? 0.f : Z * expf(nmax / p.temperature - zmax);
+    float acc_i = 0.f, dist_i = 0.f, w_i = 0.f, pos_i = 0.f;
+    for (int pp = 0; pp < p.nP; ++pp) {
+      const float s = sig[pp] / p.temperature - zmax;
+      const float logsm = s - logf(expf(s) + Zn);
+      const float dist = -logsm;
+      const float w = expf(logsm);
+      if (lane == 0) {
+        p.dists[(size_t)i * p.nP + pp] = dist;
+        p.weights[(size_t)i * p.nP + pp] = w;
+        p.pos_sim[(size_t)i * p.nP + pp] = sig[pp];
+      }
+      dist_i += dist;
+      w_i += w;
+      pos_i += sig[pp];
+      acc_i += (sig[pp] > nmax) ? 1.f : 0.f;
+    }
+    if (lane == 0) {
+      p.neg_max[i] = nmax;
+      p.row_lse[2 * i] = zmax;
+      p.row_lse[2 * i + 1] = Zn;
+    }
+    sum_dist += dist_i;
+    sum_w += w_i;
+    sum_acc += acc_i;
+    sum_pos += pos_i;
+    sum_negmax += nmax;
+  }
+  if (lane == 0) {
+    red[0][warp] = sum_dist, red[1][warp] = sum_w, red[2][warp] = sum_acc, red[3][warp] = sum_pos;
+    red[4][warp] = sum_negmax;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    float s = 0.f;
+    for (int w = 0; w < nwarps; ++w) s += red[threadIdx.x][w];
+    const float denom = threadIdx.x == 4 ? (float)p.B : (float)p.B * (float)p.nP;
+    p.scalars[threadIdx.x] = s / denom;
+  }
+}
+
+size_t infonce_workspace_bytes(int B, int D) {
+  const size_t nmb = (B + NCE_BM - 1) / NCE_BM;
+  const size_t rounded = 2 * nmb * NCE_BM * (size_t)D * sizeof(float);       // q_tf32, keys_tf32 (padded rows)
+  const size_t partials = nmb * 148 * NCE_BM * sizeof(float2);
+  return rounded + partials + 1024;
+}
+
+int infonce_fwd_launch(const InfoNceDesc& d, cudaStream_t stream) {
+  VB_REQUIRE(d.B > 0 && d.D > 0, "infonce: empty batch");
+  VB_REQUIRE(d.D % 32 == 0 && d.D <= 128, "infonce: embedding size %d unsupported (multiple of 32, <= 128)", d.D);
+  VB_REQUIRE(d.q && d.keys, "infonce: q / keys null");
+  VB_REQUIRE(d.K == 0 || d.queue_tf32, "infonce: queue pointer null");
+  VB_REQUIRE(d.Bk == d.B, "infonce: keys must have one row per query (Bk=%d, B=%d)", d.Bk, d.B);
+  VB_REQUIRE(d.num_frames >= 0 && d.num_frames <= 8, "infonce: num_frames %d unsupported", d.num_frames);
+  VB_REQUIRE(d.num_frames == 0 || d.B % d.num_frames == 0, "infonce: batch %d not a multiple of num_frames %d", d.B,
+             d.num_frames);
+  VB_REQUIRE(d.temperature > 0.f, "infonce: temperature must be positive");
+  VB_REQUIRE(d.workspace, "infonce: workspace null");
+  VB_REQUIRE((reinterpret_cast<uintptr_t>(d.workspace) & 255) == 0, "infonce: workspace must be 256-byte aligned");
+
+  const int nmb = (d.B + NCE_BM - 1) / NCE_BM;
+  const bool ibc = d.num_frames > 0;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(d.workspace);
+  float* q_r = reinterpret_cast<float*>(ws);
+  float* k_r = q_r + (size_t)nmb * NCE_BM * d.D;
+  float2* partials = reinterpret_cast<float2*>(k_r + (size_t)nmb * NCE_BM * d.D);
+
+  int rc = round_tf32_launch(d.q, q_r, (int64_t)d.B * d.D, stream);
+  if (rc) return rc;
+  if (ibc) {
+    rc = round_tf32_launch(d.keys, k_r, (int64_t)d.Bk * d.D, stream);
+    if (rc) return rc;
+  }
+
+  NceParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.B = d.B, kp.Bk = d.Bk, kp.K = d.K, kp.D = d.D, kp.nf = d.num_frames;
+  kp.nmb = nmb;
+  kp.nkt = ibc ? (d.Bk + NCE_BN - 1) / NCE_BN : 0;
+  kp.nqt = (d.K + NCE_BN - 1) / NCE_BN;
+  const int T = kp.nkt + kp.nqt;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms > 148) sms = 148;                            // partials workspace is sized for <= 148 slices
+  int slices = sms / nmb;
+  if (slices < 1) slices = 1;
+  if (slices > T) slices = T;
+  kp.slices = slices;
+  kp.scale_log2 = (float)(1.4426950408889634 / (double)d.temperature);
+  kp.partials = partials;
+
+  if (T > 0) {
+    rc = encode_tma_2d(&kp.q_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, q_r, d.D, d.B, (uint64_t)d.D * 4, 32, NCE_BM,
+                       CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    if (kp.nkt) {
+      rc = encode_tma_2d(&kp.keys_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, k_r, d.D, d.Bk, (uint64_t)d.D * 4, 32, NCE_BN,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+    if (kp.nqt) {
+      rc = encode_tma_2d(&kp.queue_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.queue_tf32, d.D, d.K, (uint64_t)d.D * 4, 32,
+                         NCE_BN, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+    const size_t q_bytes = (size_t)(d.D / 32) * NCE_BM * 128;
+    const size_t stage_bytes = (size_t)(d.D / 32) * NCE_BN * 128;
+    const size_t fixed = 1024 + q_bytes + (2 * NCE_MAX_STAGES + 5) * 8 + 16;
+    int stages = (int)((227 * 1024 - fixed) / stage_bytes);
+    if (stages > NCE_MAX_STAGES) stages = NCE_MAX_STAGES;
+    VB_REQUIRE(stages >= 2, "infonce: not enough shared memory");
+    kp.num_stages = stages;
+    const size_t smem = fixed + stages * stage_bytes;
+    VB_CHECK_CUDA(cudaFuncSetAttribute(infonce_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    infonce_main_kernel<<<nmb * slices, NCE_THREADS, smem, stream>>>(kp);
+    VB_CHECK_CUDA(cudaGetLastError());
+  }
+
+  NceFinalizeParams fp;
+  fp.q = d.q, fp.keys = d.keys, fp.partials = partials;
+  fp.B = d.B, fp.D = d.D, fp.nf = d.num_frames, fp.nP = ibc ? d.num_frames : 1;
+  fp.nmb = nmb, fp.slices = T > 0 ? slices : 0;
+  fp.temperature = d.temperature, fp.scale_log2 = kp.scale_log2;
+  fp.dists = d.dists, fp.weights = d.weights, fp.pos_sim = d.pos_sim, fp.neg_max = d.neg_max, fp.row_lse = d.row_lse;
+  fp.scalars = d.scalars;
+  infonce_finalize_kernel<<<1, 1024, 0, stream>>>(fp);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB_OK;
+}
+
+}  // namespace vb

@@ -1,0 +1,109 @@
+// Internal C++ launch API of libvince_b200 (the exported C ABI in include/vince_b200.h wraps these 1:1).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+namespace vb {
+
+// ---- conv_gemm.cu -------------------------------------------------------------------------------
+struct ConvGemmDesc {
+  const void* a_hi;      // bf16 plane(s) of A: [M,K] row-major, or NHWC [batch,H,W,Cin] when im2col
+  const void* a_lo;
+  const void* b_hi;      // bf16 plane(s) of the weights, [N, K] row-major, K ordered (r, s, cin)
+  const void* b_lo;
+  float* out;            // fp32 [M, N]
+  int M, N, K;
+  int im2col;
+  int batch, H, W, Cin, R, S, stride, pad_lo_h, pad_lo_w, pad_hi_h, pad_hi_w;
+  int passes;            // 3 = bf16x3 (fp32-grade), 1 = plain bf16
+  int block_n;           // 0 = auto
+  const float* scale;    // optional [N]
+  const float* bias;     // optional [N]
+  int relu;
+  double* stats;         // optional [2][N] (+=): per-channel sum and sum of squares of the raw outputs
+};
+int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream);
+
+// ---- elementwise.cu -----------------------------------------------------------------------------
+// Stem input packing: NCHW fp32 image -> X[n, j, q, 64] bf16 hi/lo with
+//   X[n,j,q, r2*21 + s*3 + c] = x[idx[n], c, 2j-1+r2, 2q-3+s]   (0 outside the image, 0 for e >= 42)
+// so that the 7x7/2 pad-3 stem conv becomes a 4x1 stride-1 im2col conv over j with 64 "channels".
+int stem_pack_launch(const float* x, const int64_t* gather_idx, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int H,
+                     int W, int Hj, int Q, cudaStream_t stream);
+
+struct WeightPrepEntry {   // one per weight tensor; lives in device memory
+  const float* src;        // OIHW fp32 (Linear: [Cout, Cin] with R=S=1)
+  int64_t dst_off;         // element offset into the hi / lo planes
+  int32_t Cout, Cin, R, S;
+  int32_t kind;            // 0: [Cout][R][S][Cin]; 1: stem packing [64][4][64]
+  int32_t pad;
+};
+int weight_prep_launch(const WeightPrepEntry* table_dev, int n_entries, int64_t max_elems, __nv_bfloat16* hi,
+                       __nv_bfloat16* lo, cudaStream_t stream);
+
+struct BnSide {
+  const float* raw;        // [M, C] raw conv output
+  const double* stats;     // [2][C] batch sums (train) or nullptr (eval: use running stats)
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  int64_t* num_batches_tracked;   // may be null
+};
+// out = relu?( bn(main) + residual ), residual = none | hi+lo planes | bn(second raw tensor)
+int bn_apply_launch(const BnSide& main, int res_kind, const __nv_bfloat16* res_hi, const __nv_bfloat16* res_lo,
+                    const BnSide& res_bn, int relu, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, float* out_f32,
+                    int64_t M, int C, float momentum, float eps, cudaStream_t stream);
+// stem: bn + relu + 3x3/2 pad-1 max pool, NHWC
+int bn_relu_maxpool_launch(const BnSide& bn, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int N, int P, int Q, int C,
+                           int P2, int Q2, float momentum, float eps, cudaStream_t stream);
+// last block: relu(bn(main)+residual) -> NCHW fp32 spatial features (rows scattered by scatter_idx) + global mean
+int bn_final_pool_launch(const BnSide& main, int res_kind, const __nv_bfloat16* res_hi, const __nv_bfloat16* res_lo,
+                         const BnSide& res_bn, const int64_t* scatter_idx, float* spatial_nchw, float* pooled, int N,
+                         int HW, int C, float momentum, float eps, cudaStream_t stream);
+int split_bf16_launch(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t stream);
+int l2_normalize_launch(const float* x, float* out, int rows, int D, float eps, cudaStream_t stream);
+// NCHW fp32 [N,C,H,W] -> jigsaw patches NCHW [9N,C,H3,W3] (pad bottom/right with zeros to a multiple of 3)
+int jigsaw_patchify_launch(const float* x, const int64_t* gather_idx, float* out, int N, int C, int H, int W, int H3,
+                           int W3, cudaStream_t stream);
+// out[n, j*C + c] = in[(n*9 + order[n, j]), c]
+int jigsaw_gather_launch(const float* in, const int64_t* order, float* out, int N, int C, cudaStream_t stream);
+
+struct EmaChunk {        // device-resident table, one entry per <=EMA_CHUNK contiguous elements
+  float* dst;            // key-encoder parameter
+  const float* src;      // query-encoder parameter
+  int64_t count;
+};
+constexpr int EMA_CHUNK = 8192;
+// theta_k <- m*theta_k + (1-m)*theta_q over the table, and (same launch) ring-buffer enqueue of up to two row slices
+// `one_minus` = float(1 - momentum) evaluated in double by the caller, as the reference's Python does
+int ema_enqueue_launch(const EmaChunk* table_dev, int n_chunks, float momentum, float one_minus, float* queue,
+                       float* queue_tf32, const float* keys,
+                       int64_t n0_elems, int64_t dst0_off, int64_t n1_elems, int64_t dst1_off, int64_t src1_off,
+                       cudaStream_t stream);
+
+// ---- infonce.cu ---------------------------------------------------------------------------------
+struct InfoNceDesc {
+  const float* q;          // [B, D] queries (exact fp32)
+  const float* keys;       // [Bk, D] current keys (exact fp32); Bk == B
+  const float* queue_tf32; // [K, D] queue, values pre-rounded (RN) to TF32; may be null if K == 0
+  int B, Bk, K, D;
+  int num_frames;          // > 0 (ibc): keys are the first Bk columns, positives of row i = {j : j/nf == i/nf};
+                           // 0 (MoCo): keys are NOT columns, the single positive of row i is keys[i]
+  float temperature;
+  // outputs
+  float* dists;            // [B, nP]   nP = num_frames (ibc) or 1 (MoCo)
+  float* weights;          // [B, nP]
+  float* pos_sim;          // [B, nP]   raw positive similarities
+  float* neg_max;          // [B]       max raw similarity over the negatives
+  float* row_lse;          // [B, 2]    (row max of z over all columns, Zneg relative to it) - saved for backward
+  float* scalars;          // [8]       dist, softmax_weight, nce_accuracy, cosine_sim, cosine_sim_neg_max
+  void* workspace;         // >= infonce_workspace_bytes(B, D), 256-byte aligned
+};
+size_t infonce_workspace_bytes(int B, int D);
+int infonce_fwd_launch(const InfoNceDesc& d, cudaStream_t stream);
+int round_tf32_launch(const float* x, float* out, int64_t n, cudaStream_t stream);
+
+}  // namespace vb
