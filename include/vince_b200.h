@@ -140,6 +140,13 @@ typedef struct {
 size_t vince_infonce_workspace_bytes(int32_t B, int32_t D);
 int vince_infonce_fwd(const vince_infonce_desc* desc, void* stream);
 
+/* explicit-matrix form with the literal signature of loss_util.similarity_cross_entropy (utils/loss_util.py:7-62,
+ * equal-count branch) plus the metric quantities of vince_model.py:327-333: sims [rows, cols] fp32, mask [rows, cols]
+ * bool (1 byte), exactly n_pos positives per row (else *error_flag is set to 1).  Outputs as vince_infonce_fwd. */
+int vince_masked_ce_fwd(const float* sims, const uint8_t* mask, int32_t rows, int32_t cols, int32_t n_pos,
+                        float temperature, float* dists, float* weights, float* pos_sim, float* neg_max, float* row_lse,
+                        float* scalars, int32_t* error_flag, void* stream);
+
 /* ---- fused momentum EMA (multi-tensor) + ring-buffer enqueue ----------------------------------------------------
  * replaces: VinceQueueModel.param_update (vince_model.py:587-592; ~2 launches per parameter tensor) and the
  *           copy_ calls of StorageQueue.enqueue (utils/storage_queue.py:38,46).

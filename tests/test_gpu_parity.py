@@ -1,0 +1,396 @@
+"""Parity tests proper: the CUDA path (through the reference-shaped Python API -> ctypes -> C ABI) against
+  (1) the golden vectors generated from the unmodified reference (tests/golden, oracle/make_golden.py),
+  (2) the CPU oracle (oracle/vince_oracle.py) on seeded inputs,
+  (3) size-independent properties at BASELINE.json's full sizes.
+Tolerances: 1e-3 relative on fp32 embeddings / loss (BASELINE.json north_star); bit-exact for the ring buffer;
+1e-6 relative for the EMA.  Nothing here reads /root/reference.
+"""
+import contextlib
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import vince_oracle as vo
+from conftest import make_args
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+EMB_TOL = 1e-3      # rel-L2 on embeddings (north_star)
+LOSS_TOL = 1e-3     # relative on the loss (north_star)
+
+
+def rel(a, b):
+    a = torch.as_tensor(np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a)).double()
+    b = torch.as_tensor(np.asarray(b.detach().cpu() if isinstance(b, torch.Tensor) else b)).double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def checksum(t):
+    t = t.detach().double().flatten().cpu()
+    w = torch.arange(1, t.numel() + 1, dtype=torch.float64).remainder(97.0) + 1.0
+    return np.array([t.sum().item(), (t * w).sum().item(), t.abs().sum().item()])
+
+
+def sd_checksum(sd):
+    acc = np.zeros(3)
+    for v in sd.values():
+        if v.is_floating_point():
+            acc += checksum(v)
+    return acc
+
+
+@contextlib.contextmanager
+def injected_randperm(perms):
+    real = torch.randperm
+    it = iter(perms)
+
+    def fake(n, *a, **k):
+        p = next(it)
+        assert p.numel() == n
+        dev = k.get("device", None)
+        return p.clone().to(dev) if dev is not None else p.clone()
+
+    torch.randperm = fake
+    try:
+        yield
+    finally:
+        torch.randperm = real
+
+
+def build_model(backbone, nf, B, K, D, T=0.07, seed=0, jigsaw=False, ibc=True, self_cmp=False, passes=3):
+    import vince_b200
+    args = make_args(backbone=backbone, num_frames=nf, batch_size=B, queue_size=K, embedding_size=D, temperature=T,
+                     jigsaw=jigsaw, inter_batch_comparison=ibc, self_batch_comparison=self_cmp, device=DEV, passes=passes)
+    model = vince_b200.VinceModel(args)
+    sd = vo.make_state_dict(backbone, D, jigsaw=jigsaw, seed=seed)
+    model.load_state_dict(sd, strict=True)
+    model.to(DEV)
+    model.train()
+    return args, model, sd
+
+
+# ----------------------------------------------------------------------------------------------------------
+# encoder vs golden vectors from the reference
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case,backbone", [("r18_64", "ResNet18"), ("r50_64", "ResNet50"), ("r18_odd", "ResNet18")])
+def test_encoder_matches_reference_golden(golden, case, backbone):
+    g = golden("encoder.npz")
+    B, nf, H, W, D, seed, shuffle = [int(v) for v in g[case + "/cfg"]]
+    args, model, sd = build_model(backbone, nf, B, 64, D, seed=seed)
+    np.testing.assert_allclose(sd_checksum(sd), g[case + "/weights_checksum"], rtol=1e-9)
+    x = torch.from_numpy(g[case + "/x"]).to(DEV)
+    inputs = {"data": x, "batch_types": ["images"], "batch_sizes": [B]}
+    if shuffle:
+        with injected_randperm([torch.from_numpy(g[case + "/perm"])]):
+            r = model.get_embeddings(inputs, shuffle=True)[0]
+    else:
+        r = model.get_embeddings(inputs, shuffle=False)[0]
+    torch.cuda.synchronize()
+    assert rel(r["embeddings"], g[case + "/embeddings"]) < EMB_TOL
+    assert rel(r["prenorm_features"], g[case + "/prenorm_features"]) < EMB_TOL
+    # intermediate features are looser than the north-star quantities (embeddings / loss): these golden cases are
+    # deliberately ill-conditioned (B=4 at 64x64 leaves 16 samples per channel for layer4's batch statistics, and a
+    # random-init ResNet-50 amplifies rounding ~20x) and the reference's own fp32 result is itself
+    # ~1e-4 away from an fp64 evaluation of the same network.
+    feat_tol = 3 * EMB_TOL if backbone == "ResNet50" else EMB_TOL
+    assert rel(r["extracted_features"], g[case + "/extracted_features"]) < feat_tol
+    assert rel(r["spatial_features"], g[case + "/spatial_features"]) < feat_tol
+    assert r["spatial_features"].shape == g[case + "/spatial_features"].shape
+    post = model.state_dict()
+    assert rel(post["feature_extractor.module.model.bn1.running_mean"], g[case + "/bn1_running_mean"]) < 1e-4
+    assert rel(post["feature_extractor.module.model.bn1.running_var"], g[case + "/bn1_running_var"]) < 1e-4
+    last_rv = [k for k in post if k.endswith("running_var")][-1]
+    assert rel(post[last_rv], g[case + "/last_bn_running_var"]) < 1e-3
+    assert int(post["feature_extractor.module.model.bn1.num_batches_tracked"]) == int(g[case + "/bn1_num_batches"])
+    # eval-mode BN with the updated running statistics
+    model.eval()
+    r_eval = model.get_embeddings({"data": x})
+    torch.cuda.synchronize()
+    assert rel(r_eval["embeddings"], g[case + "/eval_embeddings"]) < EMB_TOL
+    assert rel(r_eval["extracted_features"], g[case + "/eval_extracted_features"]) < feat_tol
+
+
+def test_ema_matches_reference_golden(golden):
+    import vince_b200
+    g = golden("encoder.npz")
+    case = "r18_64"
+    B, nf, H, W, D, seed, shuffle = [int(v) for v in g[case + "/cfg"]]
+    args, model, sd = build_model("ResNet18", nf, B, 64, D, seed=seed)
+    # the golden EMA was taken after one train-mode forward (BN stats are not EMA'd, so only weights matter)
+    qm = vince_b200.VinceQueueModel(args, model)
+    qm.to(DEV)
+    with torch.no_grad():
+        for i, p in enumerate(model.vince_parameters()):
+            p.add_(0.01 * ((i % 7) - 3))
+    qm.param_update(model, 0.999)
+    torch.cuda.synchronize()
+    key_params = qm.queue_network.vince_parameters()
+    n_tensors, n_elems = [int(v) for v in g[case + "/ema_n_tensors"]]
+    assert len(key_params) == n_tensors and sum(p.numel() for p in key_params) == n_elems
+    np.testing.assert_allclose(sum(checksum(p) for p in key_params), g[case + "/ema_checksum"], rtol=1e-6)
+    got = dict(qm.queue_network.named_parameters())["embedding.2.bias"]
+    assert rel(got, g[case + "/ema_embedding2_bias"]) < 1e-6
+    # momentum 0 == hard copy (vince_solver.py:296,318)
+    qm.param_update(model, 0.0)
+    torch.cuda.synchronize()
+    for a, b in zip(qm.queue_network.vince_parameters(), model.vince_parameters()):
+        assert torch.equal(a, b)
+
+
+def test_jigsaw_matches_reference_golden(golden):
+    g = golden("jigsaw.npz")
+    case = "r18_jigsaw"
+    B, nf, H, W, D, seed = [int(v) for v in g[case + "/cfg"]]
+    args, model, sd = build_model("ResNet18", nf, B, 64, D, seed=seed, jigsaw=True)
+    np.testing.assert_allclose(sd_checksum(sd), g[case + "/weights_checksum"], rtol=1e-9)
+    x = torch.from_numpy(g[case + "/x"]).to(DEV)
+    perm = torch.from_numpy(g[case + "/perm"])
+    orders = torch.from_numpy(g[case + "/orders"])
+    with injected_randperm([perm] + list(orders)):
+        r = model.get_embeddings({"data": x, "batch_types": ["images"], "batch_sizes": [B]}, jigsaw=True, shuffle=True)[0]
+    torch.cuda.synchronize()
+    assert rel(r["embeddings"], g[case + "/embeddings"]) < EMB_TOL
+    assert rel(r["prenorm_features"], g[case + "/prenorm_features"]) < EMB_TOL
+
+
+# ----------------------------------------------------------------------------------------------------------
+# InfoNCE vs golden vectors from the reference
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["ibc_nf4", "ibc_nf2", "ibc_nf1", "ibc_self_nf4", "moco", "ibc_short_batch"])
+def test_infonce_matches_reference_golden(golden, case):
+    import vince_b200
+    g = golden("infonce.npz")
+    B, K, D, nf, ibc, self_cmp, Bact = [int(v) for v in g[case + "/cfg"]]
+    T, T_self = [float(v) for v in g[case + "/T"]]
+    args = make_args(num_frames=nf, batch_size=B, queue_size=K, embedding_size=D, temperature=T, self_temperature=T_self,
+                     inter_batch_comparison=bool(ibc), self_batch_comparison=bool(self_cmp), device=DEV)
+    model = vince_b200.VinceModel.__new__(vince_b200.VinceModel)          # loss path never touches the network
+    torch.nn.Module.__init__(model)
+    model.args, model.num_frames, model.launches, model._device = args, nf, 0, DEV
+    q = torch.from_numpy(g[case + "/q"]).to(DEV)
+    k = torch.from_numpy(g[case + "/k"]).to(DEV)
+    queue = torch.from_numpy(g[case + "/queue"]).to(DEV)
+    inputs = {"extracted_features": q, "embeddings": q, "queue_embeddings": k, "queue_vectors": queue,
+              "data_source": "synthetic", "num_frames": nf}
+    out = model(inputs)
+    losses = model.loss(out)
+    metrics = model.get_metrics(out)
+    torch.cuda.synchronize()
+    ref_loss = float(g[case + "/nce_loss"])
+    assert abs(float(losses["nce_loss"][1]) - ref_loss) / abs(ref_loss) < LOSS_TOL
+    assert losses["nce_loss"][0] == 1.0
+    assert out["vince_loss_dists"].shape == g[case + "/dists"].shape
+    assert rel(out["vince_loss_dists"], g[case + "/dists"]) < LOSS_TOL
+    assert rel(out["vince_loss_softmax_weights"], g[case + "/softmax_weights"]) < 5e-3
+    assert abs(float(out["vince_loss_softmax_weight"]) - float(g[case + "/softmax_weight"])) < 5e-3 * max(
+        float(g[case + "/softmax_weight"]), 1e-6)
+    for name in ("nce_accuracy_mean", "cosine_sim", "cosine_sim_neg_max", "nce_softmax_weight_mean"):
+        ref_v = float(g[case + "/metric_" + name])
+        assert abs(float(metrics[name]) - ref_v) < 1e-3 * max(abs(ref_v), 1.0), name
+    if self_cmp:
+        ref_self = float(g[case + "/nce_loss_self"])
+        assert abs(float(losses["nce_loss_self"][1]) - ref_self) / abs(ref_self) < LOSS_TOL
+        assert rel(out["vince_loss_self_dists"], g[case + "/self_dists"]) < LOSS_TOL
+    # the lazily materialised similarity matrix equals the reference's
+    sims = out["vince_similarities"].materialize()
+    assert rel(sims, g[case + "/similarities"]) < 1e-4
+    # explicit-matrix API (loss_util.similarity_cross_entropy's literal signature)
+    mask = torch.from_numpy(g[case + "/mask"]).to(DEV)
+    ce = vince_b200.loss_util.similarity_cross_entropy(torch.from_numpy(g[case + "/similarities"]).to(DEV), T,
+                                                       q.shape[0], 1, mask)
+    torch.cuda.synchronize()
+    assert abs(float(ce["dist"]) - ref_loss) / abs(ref_loss) < 1e-5
+    assert rel(ce["dists"], g[case + "/dists"]) < 1e-5
+    assert rel(ce["softmax_weights"], g[case + "/softmax_weights"]) < 1e-4
+
+
+# ----------------------------------------------------------------------------------------------------------
+# queue ring buffer: bit-exact vs the reference's StorageQueue
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["exact_multiple", "ragged", "bigger_than_queue"])
+def test_queue_matches_reference_golden(golden, case):
+    import vince_b200
+    g = golden("queue.npz")
+    init = torch.from_numpy(g[case + "/init"])
+    K, D = init.shape
+    q = vince_b200.StorageQueue(K, D, device=DEV)
+    assert q.maxsize == K and len(q) == K and q.current_tail == 0 and q.full is False
+    assert rel(q.vector_queue.norm(dim=1), torch.ones(K)) < 1e-6       # unit-norm random init
+    q.load(init.to(DEV))
+    for i, n in enumerate(g[case + "/sizes"]):
+        items = torch.from_numpy(g["%s/items%d" % (case, i)]).to(DEV)
+        q.enqueue(items, [i] * int(n), "src")
+        torch.cuda.synchronize()
+        assert torch.equal(q.dequeue()["queue_vectors"].cpu(), torch.from_numpy(g["%s/queue%d" % (case, i)])), i
+        tail, full = g["%s/state%d" % (case, i)]
+        assert q.current_tail == int(tail) and q.full == bool(full)
+        # TF32 shadow stays coherent with the fp32 queue
+        shadow = q.dequeue()["queue_vectors_tf32"]
+        assert rel(shadow, q.vector_queue) < 3e-4
+        assert bool(((shadow.view(torch.int32) & 0x1FFF) == 0).all())
+    assert q.data_source_queue[q.current_tail - 1 if q.current_tail else K - 1] == "src"
+    q.clear()
+    assert q.current_tail == 0 and q.full is False
+
+
+# ----------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[0]: one full scoring step at 224x224 vs the reference's outputs
+# ----------------------------------------------------------------------------------------------------------
+def test_full_step_cfg0_matches_reference_golden(golden):
+    import vince_b200
+    g = golden("step_cfg0.npz")
+    B, nf, K, D = [int(v) for v in g["cfg"]]
+    T, m = [float(v) for v in g["T_m"]]
+    args, model, sd = build_model("ResNet18", nf, B, K, D, T=T, seed=0)
+    np.testing.assert_allclose(sd_checksum(sd), g["weights_checksum"], rtol=1e-9)
+    qm = vince_b200.VinceQueueModel(args, model)
+    qm.to(DEV)
+    qm.train()
+    gen = torch.Generator().manual_seed(1234)
+    data = torch.randn((B, 3, 224, 224), generator=gen)
+    queue_data = torch.randn((B, 3, 224, 224), generator=gen)
+    queue_init = F.normalize(torch.randn((K, D), generator=gen), dim=-1)
+    np.testing.assert_allclose(checksum(data), g["data_checksum"], rtol=1e-9)
+    np.testing.assert_allclose(checksum(queue_data), g["queue_data_checksum"], rtol=1e-9)
+    np.testing.assert_allclose(checksum(queue_init), g["queue_init_checksum"], rtol=1e-9)
+    queue = vince_b200.StorageQueue(K, D, device=DEV)
+    queue.load(queue_init.to(DEV))
+    queue.current_tail = K - 3
+    batch = {"data": data.to(DEV), "queue_data": queue_data.to(DEV), "batch_types": ["images"], "batch_sizes": [B],
+             "data_source": "synthetic", "num_frames": nf}
+    # --- vince_solver.py:405-428 ---
+    with injected_randperm([torch.from_numpy(g["perm_k"]), torch.from_numpy(g["perm_q"])]):
+        queue_batches = qm(batch, shuffle=True)
+        outputs = model.get_embeddings(batch, shuffle=True)
+    output = outputs[0]
+    output.update(queue.dequeue())
+    output.update({"data_source": "synthetic", "num_frames": nf})
+    output.update(queue_batches[0])
+    output.update(model(output))
+    loss = model.loss(output)
+    metrics = model.get_metrics(output)
+    # --- :497-499 ---
+    queue.enqueue(output["queue_embeddings"], [None] * B, "synthetic")
+    qm.vince_update(model)
+    torch.cuda.synchronize()
+    assert rel(output["embeddings"], g["embeddings"]) < EMB_TOL
+    assert rel(output["queue_embeddings"], g["queue_embeddings"]) < EMB_TOL
+    assert rel(output["extracted_features"], g["extracted_features"]) < EMB_TOL
+    ref_loss = float(g["loss"])
+    assert abs(float(loss["nce_loss"][1]) - ref_loss) / abs(ref_loss) < LOSS_TOL
+    assert rel(output["vince_loss_dists"], g["dists"]) < LOSS_TOL
+    for name in ("nce_accuracy_mean", "cosine_sim", "cosine_sim_neg_max", "nce_softmax_weight_mean"):
+        ref_v = float(g["metric_" + name])
+        assert abs(float(metrics[name]) - ref_v) < 2e-3 * max(abs(ref_v), 1.0), name
+    tail, full = [int(v) for v in g["queue_state"]]
+    assert queue.current_tail == tail and queue.full == bool(full)
+    assert rel(queue.vector_queue[K - 3:], g["queue_tail_rows"]) < EMB_TOL
+    assert rel(queue.vector_queue[:B], g["queue_head_rows"]) < EMB_TOL
+    # rows that were not overwritten are bit-identical to the initial queue
+    assert torch.equal(queue.vector_queue[B:K - 3].cpu(), queue_init[B:K - 3])
+    np.testing.assert_allclose(sum(checksum(p) for p in qm.queue_network.vince_parameters()), g["ema_checksum"],
+                               rtol=1e-6)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CUDA path vs the CPU oracle on seeded inputs (fp64 oracle = "truth")
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("backbone,B,H,passes,tol", [("ResNet18", 16, 96, 3, EMB_TOL), ("ResNet50", 8, 64, 3, EMB_TOL),
+                                                    ("ResNet18", 16, 96, 1, 5e-2)])
+def test_encoder_vs_fp64_oracle(backbone, B, H, passes, tol):
+    args, model, sd = build_model(backbone, 4, B, 64, 128, seed=5, passes=passes)
+    gen = torch.Generator().manual_seed(77)
+    x = torch.randn((B, 3, H, H), generator=gen)
+    ref = vo.get_embeddings(x.double(), vo.clone_state_dict(sd, torch.float64), backbone, True)
+    r = model.get_embeddings({"data": x.to(DEV)})
+    torch.cuda.synchronize()
+    err = rel(r["embeddings"], ref["embeddings"])
+    print("%s passes=%d embedding rel-L2 vs fp64 oracle: %.3e" % (backbone, passes, err))
+    assert err < tol
+
+
+def test_fused_update_equals_separate_calls():
+    """VinceQueueModel.vince_update(model, enqueue=...) (one launch) == enqueue() + vince_update() (reference order)."""
+    import vince_b200
+    args, model, sd = build_model("ResNet18", 2, 8, 40, 32, seed=2)
+    gen = torch.Generator().manual_seed(3)
+    init = F.normalize(torch.randn((40, 32), generator=gen), dim=-1).to(DEV)
+    keys = [F.normalize(torch.randn((8, 32), generator=gen), dim=-1).to(DEV) for _ in range(7)]
+    res = []
+    for fused in (False, True):
+        qm = vince_b200.VinceQueueModel(args, model)
+        qm.to(DEV)
+        with torch.no_grad():
+            for p in qm.queue_network.vince_parameters():
+                p.mul_(0.5)
+        queue = vince_b200.StorageQueue(40, 32, device=DEV)
+        queue.load(init)
+        queue.current_tail = 5
+        for kk in keys:
+            if fused:
+                qm.vince_update(model, enqueue=(queue, kk, [None] * 8, "s"))
+            else:
+                queue.enqueue(kk, [None] * 8, "s")
+                qm.vince_update(model)
+        torch.cuda.synchronize()
+        res.append((queue.vector_queue.clone(), queue.current_tail, queue.full,
+                    [p.clone() for p in qm.queue_network.vince_parameters()]))
+    assert torch.equal(res[0][0], res[1][0]) and res[0][1:3] == res[1][1:3]
+    for a, b in zip(res[0][3], res[1][3]):
+        assert torch.equal(a, b)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs[1]/[2] sizes)
+# ----------------------------------------------------------------------------------------------------------
+def test_infonce_full_size_vs_fp64_oracle():
+    """B=256, K=65536, D=128, nf=4 (cfg1/cfg2 InfoNCE shape): fused kernel vs the fp64 oracle on the same bits."""
+    from vince_b200 import ops
+    gen = torch.Generator().manual_seed(99)
+    B, K, D, nf = 256, 65536, 128, 4
+    for T in (0.07, 0.2):
+        q = F.normalize(torch.randn((B, D), generator=gen), dim=1)
+        k = F.normalize(q + 0.8 * torch.randn((B, D), generator=gen), dim=1)
+        queue = F.normalize(torch.randn((K, D), generator=gen), dim=1)
+        losses, metrics, ex = vo.infonce(q.double(), k.double(), queue.double(), nf, T)
+        qd, kd, qud = q.to(DEV), k.to(DEV), queue.to(DEV)
+        qt = torch.empty_like(qud)
+        ops.round_tf32(qud, qt)
+        out = ops.infonce_fwd(qd, kd, qt, nf, T)
+        torch.cuda.synchronize()
+        sc = out["scalars"].cpu()
+        assert abs(sc[0].item() - losses["nce_loss"].item()) / losses["nce_loss"].item() < 1e-4
+        assert rel(out["dists"], ex["vince_loss_dists"].reshape(B, nf)) < 1e-4
+        assert abs(sc[4].item() - metrics["cosine_sim_neg_max"].item()) < 1e-4
+        assert abs(sc[3].item() - metrics["cosine_sim"].item()) < 1e-6
+        # permutation invariance of the negatives: shuffling queue rows must not change the loss
+        perm = torch.randperm(K, generator=gen)
+        out2 = ops.infonce_fwd(qd, kd, qt[perm.to(DEV)].contiguous(), nf, T)
+        torch.cuda.synchronize()
+        assert abs(out2["scalars"][0].item() - sc[0].item()) < 1e-5 * abs(sc[0].item())
+        assert torch.allclose(out2["neg_max"], out["neg_max"], atol=0, rtol=0)
+
+
+def test_encoder_full_batch_eval_is_batch_separable():
+    """Eval-mode BN makes frames independent: a B=256 224x224 ResNet-18 forward must equal, row for row, the same
+    frames pushed through in two halves (exercises every tile-scheduling path at the benchmark's full size)."""
+    args, model, sd = build_model("ResNet18", 4, 256, 64, 128, seed=1)
+    model.eval()
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn((256, 3, 224, 224), generator=gen).to(DEV)
+    full = model.get_embeddings({"data": x})["embeddings"]
+    a = model.get_embeddings({"data": x[:128].contiguous()})["embeddings"]
+    b = model.get_embeddings({"data": x[128:].contiguous()})["embeddings"]
+    torch.cuda.synchronize()
+    assert torch.isfinite(full).all()
+    assert rel(full, torch.cat((a, b))) < 1e-6
+    assert rel(full.norm(dim=1), torch.ones(256)) < 1e-6
+
+
+def test_ops_reject_cpu_tensors():
+    from vince_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.l2_normalize(torch.zeros(4, 8), torch.zeros(4, 8))

@@ -135,6 +135,15 @@ int vince_infonce_fwd(const vince_infonce_desc* d, void* stream) {
   return infonce_fwd_launch(n, S(stream));
 }
 
+int vince_masked_ce_fwd(const float* sims, const uint8_t* mask, int32_t rows, int32_t cols, int32_t n_pos,
+                        float temperature, float* dists, float* weights, float* pos_sim, float* neg_max, float* row_lse,
+                        float* scalars, int32_t* error_flag, void* stream) {
+  VB_REQUIRE(sims && mask && dists && weights && pos_sim && neg_max && row_lse && scalars && error_flag,
+             "vince_masked_ce_fwd: null pointer");
+  return masked_ce_launch(sims, mask, rows, cols, n_pos, temperature, dists, weights, pos_sim, neg_max, row_lse, scalars,
+                          error_flag, S(stream));
+}
+
 int vince_ema_enqueue(const vince_ema_chunk* table_dev, int32_t n_chunks, float momentum, float one_minus_momentum,
                       float* queue, float* queue_tf32, const float* keys, int64_t n0, int64_t dst0, int64_t n1,
                       int64_t dst1, int64_t src1, void* stream) {

@@ -105,5 +105,10 @@ struct InfoNceDesc {
 size_t infonce_workspace_bytes(int B, int D);
 int infonce_fwd_launch(const InfoNceDesc& d, cudaStream_t stream);
 int round_tf32_launch(const float* x, float* out, int64_t n, cudaStream_t stream);
+// explicit-matrix masked cross entropy (loss_util.similarity_cross_entropy's literal signature); error_flag is set
+// to 1 when some row does not have exactly nP positives
+int masked_ce_launch(const float* sims, const uint8_t* mask, int R, int C, int nP, float temperature, float* dists,
+                     float* weights, float* pos_sim, float* neg_max, float* row_lse, float* scalars, int* error_flag,
+                     cudaStream_t stream);
 
 }  // namespace vb

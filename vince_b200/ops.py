@@ -8,6 +8,7 @@ from . import _lib
 
 BN_MOMENTUM = 0.1
 BN_EPS = 1e-5
+PROFILE = None      # set to a list by bench.py to collect (name, algorithmic flops, start_event, end_event)
 
 
 def _stream():
@@ -66,6 +67,15 @@ def conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, block_n=
     d.bias = _ptr(bias, torch.float32, "bias").value if bias is not None else None
     d.relu = 1 if relu else 0
     d.stats = _ptr(stats, torch.float64, "stats").value if stats is not None else None
+    if PROFILE is not None:
+        # bench.py's roofline leg: CUDA events around every tensor-core launch, on the launching stream
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(_lib.lib().vince_conv_fwd(ctypes.byref(d), _stream()), "vince_conv_fwd")
+        e1.record()
+        k_true = geom.get("K_true", K) if geom is not None else K
+        PROFILE.append(("conv_gemm", 2.0 * M * N * k_true, e0, e1))
+        return
     _lib.check(_lib.lib().vince_conv_fwd(ctypes.byref(d), _stream()), "vince_conv_fwd")
 
 
@@ -75,7 +85,7 @@ def stem_geometry(H, W):
     Hj = H // 2 + 1
     return dict(P=P, Q=Q, Hj=Hj,
                 geom=dict(H=Hj, W=Q, Cin=64, R=4, S=1, stride=1, pad_lo_h=1, pad_lo_w=0, pad_hi_h=P + 2 - Hj,
-                          pad_hi_w=0))
+                          pad_hi_w=0, K_true=147))      # algorithmic K of the 7x7x3 stem (the packed K is 256)
 
 
 def stem_pack(x, gather_idx, x_hi, x_lo):

@@ -1,0 +1,499 @@
+"""VinceModel / VinceQueueModel on B200: the reference's API surface, hand-written sm_100a kernels underneath.
+
+Drop-in for /root/reference/models/vince_model.py:19-349 (VinceModel) and :573-613 (VinceQueueModel) as used by
+solvers/vince_solver.py:267-291,386-518: same constructor (`args`), attributes (`num_frames`, `output_channels`,
+`feature_extractor.module`, `embedding`, `device`), methods and dict keys.  What changes is how the
+work is done:
+
+  get_embeddings   stem pack (+shuffle gather) -> tcgen05 implicit-GEMM convs with train-mode BN -> fused
+                   relu(bn+residual)+avg-pool (+un-shuffle scatter) -> tcgen05 projection MLP -> L2 normalise
+  forward/loss/    ONE fused InfoNCE kernel over [keys || queue]; the [B, B+K] similarity matrix is never written.
+  get_metrics      `vince_similarities` / `vince_l_neg` in the returned dict are LazySimilarity handles that
+                   materialise (through the same GEMM kernel) only if somebody asks.
+  param_update     one multi-tensor EMA launch (optionally fused with the queue enqueue)
+
+Forward only: autograd does not flow through the CUDA path (the query-encoder backward is SURVEY.md 8f rank 1,
+not built yet); `loss()` returns detached tensors.
+"""
+import copy
+import os
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import loss_util, ops
+from .backbone_models import DataParallelShim
+from .encoder import HeadRunner
+
+
+def _device_of(t):
+    return t if isinstance(t, torch.device) else torch.device(t)
+
+
+class BaseModel(nn.Module):
+    """Stand-in for dg_util's pt_util.BaseModel + models/base_model.py:8-26 (device bookkeeping, save/restore)."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self._device = "cpu"
+        self.saves = 0
+
+    @property
+    def device(self):
+        return self._device
+
+    def to(self, device):
+        self._device = device
+        super().to(device)
+
+    def restore(self, skip_filter=None) -> int:
+        """models/base_model.py:13-19: returns the iteration encoded in the newest checkpoint name (0 if none)."""
+        if not getattr(self.args, "restore", False):
+            return 0
+        ckpt_dir = self.args.checkpoint_dir
+        if not os.path.isdir(ckpt_dir):
+            return 0
+        files = sorted(f for f in os.listdir(ckpt_dir) if f.endswith(".pt"))
+        if not files:
+            return 0
+        path = os.path.join(ckpt_dir, files[-1])
+        state = torch.load(path, map_location="cpu")
+        if skip_filter is not None:
+            state = {k: v for k, v in state.items() if not skip_filter(k)}
+        self.load_state_dict(state, strict=False)
+        try:
+            return int(os.path.splitext(files[-1])[0].split("_")[-1])
+        except ValueError:
+            return 0
+
+    def save(self, iteration, num_to_keep=1):
+        if not getattr(self.args, "save", False):
+            return
+        os.makedirs(self.args.checkpoint_dir, exist_ok=True)
+        torch.save(self.state_dict(), os.path.join(self.args.checkpoint_dir, "%s_%010d.pt" % (type(self).__name__, iteration)))
+        files = sorted(f for f in os.listdir(self.args.checkpoint_dir) if f.endswith(".pt"))
+        if num_to_keep > 0:
+            for f in files[:-num_to_keep]:
+                os.remove(os.path.join(self.args.checkpoint_dir, f))
+        self.saves += 1
+
+
+class LazySimilarity:
+    """Handle for a similarity matrix the fused kernel never wrote (vince_model.py:224,229-230 would).
+    `.materialize()` computes q @ cols^T with the tcgen05 GEMM kernel and caches it."""
+
+    def __init__(self, q, col_blocks, passes=3, prefix=None):
+        self.q, self.col_blocks, self.passes = q, [c for c in col_blocks if c is not None and c.shape[0] > 0], passes
+        self.prefix = prefix          # already-computed leading columns (MoCo's l_pos, vince_model.py:227-230)
+        self.shape = (q.shape[0], sum(c.shape[0] for c in self.col_blocks) + (prefix.shape[1] if prefix is not None else 0))
+        self._value = None
+
+    def materialize(self):
+        if self._value is None:
+            B, D = self.q.shape
+            dev = self.q.device
+            Dp = (D + 63) // 64 * 64               # the GEMM wants K % 64 == 0: zero-pad the feature dim
+            with torch.cuda.device(dev):
+                def planes(x):
+                    if Dp != D:
+                        xp = torch.zeros((x.shape[0], Dp), device=dev, dtype=torch.float32)
+                        xp[:, :D] = x
+                        x = xp
+                    hi = torch.empty(x.shape, device=dev, dtype=torch.bfloat16)
+                    lo = torch.empty_like(hi)
+                    ops.split_bf16(x.contiguous(), hi, lo)
+                    return hi, lo
+                q_hi, q_lo = planes(self.q)
+                outs = []
+                for cols in self.col_blocks:
+                    n = cols.shape[0]
+                    n_pad = (n + 31) // 32 * 32
+                    c_hi, c_lo = planes(cols)
+                    if n_pad != n:
+                        pad = torch.zeros((n_pad - n, Dp), device=dev, dtype=torch.bfloat16)
+                        c_hi, c_lo = torch.cat((c_hi, pad)), torch.cat((c_lo, pad))
+                    out = torch.empty((B, n_pad), device=dev, dtype=torch.float32)
+                    ops.conv_fwd(q_hi, q_lo, c_hi, c_lo, out, B, n_pad, Dp, passes=3)
+                    outs.append(out[:, :n])
+                if self.prefix is not None:
+                    outs.insert(0, self.prefix)
+                self._value = outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
+        return self._value
+
+    def __repr__(self):
+        return "LazySimilarity(shape=%s, materialized=%s)" % (self.shape, self._value is not None)
+
+
+class VinceModel(BaseModel):
+    def __init__(self, args):
+        super(VinceModel, self).__init__(args)
+        self.args = args
+        self.num_frames = self.args.num_frames
+        passes = getattr(args, "vince_b200_passes", 3)
+        self.passes = passes
+
+        self.feature_extractor = self.args.backbone(self.args, -2)
+        resnet_output_channels = self.feature_extractor.output_channels
+        self.output_channels = resnet_output_channels
+        if getattr(self.args, "use_attention", False):
+            raise NotImplementedError("--use-attention is not used by any reference config and is not implemented")
+        # average_layers has no parameters in the reference either (AdaptiveAvgPool2d + RemoveDim, vince_model.py:33);
+        # the pooling itself is fused into the last residual block's epilogue kernel.
+        self.average_layers = nn.Sequential()
+        self.feature_extractor = DataParallelShim(self.feature_extractor)
+        self.feature_extractor_device = args.feature_extractor_gpu_ids[0]
+
+        self.embedding = nn.Sequential(
+            nn.Linear(self.output_channels, self.output_channels),
+            nn.ReLU(inplace=True),
+            nn.Linear(self.output_channels, self.args.vince_embedding_size),
+        )
+        self._heads = {"embedding": HeadRunner([self.embedding[0], self.embedding[2]], passes)}
+        if self.args.jigsaw:
+            self.jigsaw_linear = nn.Linear(self.output_channels, self.output_channels)
+            self.jigsaw_embedding = nn.Sequential(
+                nn.Linear(self.output_channels * 9, self.output_channels),
+                nn.ReLU(inplace=True),
+                nn.Linear(self.output_channels, self.args.vince_embedding_size),
+            )
+            self._heads["jigsaw"] = HeadRunner([self.jigsaw_linear, self.jigsaw_embedding[0], self.jigsaw_embedding[2]],
+                                               passes)
+        if getattr(self.args, "use_imagenet", False):
+            raise NotImplementedError("--use-imagenet decoders are outside the hot path and are not implemented")
+        self.launches = 0
+
+    # the [B, B+K] boolean masks of vince_model.py:50-77 are only ever handed to the loss; build them on demand
+    def _mask(self, n_rows, n_cols, num_frames, device):
+        idx = torch.arange(n_rows, device=device) // max(num_frames, 1)
+        m = torch.zeros((n_rows, n_cols), dtype=torch.bool, device=device)
+        m[:, :n_rows] = idx[:, None] == idx[None, :]
+        return m
+
+    @property
+    def similarity_mask(self):
+        return self._mask(self.args.batch_size, self.args.batch_size + self.args.vince_queue_size, self.num_frames,
+                          self.device)
+
+    @property
+    def eye_mask(self):
+        return self._mask(self.args.batch_size, self.args.batch_size + self.args.vince_queue_size, 1, self.device)
+
+    def to(self, device):
+        super(VinceModel, self).to(device)
+        self.feature_extractor.to(self.feature_extractor_device if str(self.feature_extractor_device) != "cpu" else device)
+
+    def vince_parameters(self):
+        params = (list(self.feature_extractor.parameters()) + list(self.embedding.parameters())
+                  + list(self.average_layers.parameters()))
+        if self.args.jigsaw:
+            params += list(self.jigsaw_linear.parameters()) + list(self.jigsaw_embedding.parameters())
+        return params
+
+    @staticmethod
+    def split_dict_by_type(batch_types, batch_sizes, dict_to_split):
+        # vince_model.py:106-121, verbatim semantics (incl. the len(val) == len(batch_types) quirk)
+        num_total = 0
+        mini_batch_list = []
+        assert "queue_vectors" not in dict_to_split
+        for ind, (batch_type, batch_size) in enumerate(zip(batch_types, batch_sizes)):
+            mini_batch = {
+                key: (val[ind] if len(val) == len(batch_types) else val[num_total: num_total + batch_size])
+                for key, val in dict_to_split.items()
+            }
+            mini_batch["batch_type"] = batch_type
+            mini_batch.pop("batch_types", None)
+            mini_batch_list.append(mini_batch)
+            num_total += batch_size
+        return mini_batch_list
+
+    def extract_features(self, inputs, run_average_layer=True, gather_idx=None, scatter_idx=None):
+        return_val = {}
+        spatial, pooled = self.feature_extractor(inputs, gather_idx=gather_idx, scatter_idx=scatter_idx,
+                                                 want_pooled=True)
+        self.launches += self.feature_extractor.module.runner.launches
+        return_val["spatial_features"] = spatial
+        if run_average_layer:
+            return_val["extracted_features"] = pooled
+        return return_val
+
+    def get_embeddings(self, inputs, jigsaw=False, shuffle=False, jigsaw_orders=None):
+        """vince_model.py:135-196.  `jigsaw_orders` ([N,9] int64, optional) replaces the per-row randperm(9) draw."""
+        self.launches = 0
+        with torch.no_grad():
+            data = inputs["data"]
+            if not data.is_cuda:
+                raise RuntimeError("vince_b200.VinceModel: input batch must already be on the GPU (the solver's "
+                                   "prefetch thread does the H2D copy, vince_solver.py:352-355); no CPU fallback")
+            n = data.shape[0]
+            shuffle_order = None
+            if shuffle:
+                shuffle_order = torch.randperm(n, device=data.device)          # vince_model.py:139
+            with torch.cuda.device(data.device):
+                if jigsaw:
+                    return_val = self._jigsaw_embeddings(data, shuffle_order, jigsaw_orders)
+                else:
+                    # shuffle gather folded into the stem's loads, un-shuffle into the last block's stores
+                    return_val = self.extract_features(data.float() if data.dtype != torch.float32 else data,
+                                                       gather_idx=shuffle_order, scatter_idx=shuffle_order)
+                    head = self._heads["embedding"]
+                    head.refresh()
+                    hidden = head.linear(0, return_val["extracted_features"], relu=True)
+                    output = head.linear(1, hidden, relu=False)
+                    self.launches += head.launches
+                    return_val["prenorm_features"] = output
+                    emb = torch.empty_like(output)
+                    ops.l2_normalize(output, emb)
+                    self.launches += 1
+                    return_val["embeddings"] = emb
+        if "batch_types" in inputs:
+            return_val = self.split_dict_by_type(inputs["batch_types"], inputs["batch_sizes"], return_val)
+        return return_val
+
+    def _jigsaw_embeddings(self, data, shuffle_order, jigsaw_orders):
+        # vince_model.py:144-173.  On one device the batch shuffle only permutes rows, so instead of gathering the
+        # images we keep them in place and move the per-row patch permutations to their un-shuffled rows.
+        N, C, H, W = data.shape
+        dev = data.device
+        Hp = H + (3 - H % 3) % 3
+        Wp = W + (3 - W % 3) % 3
+        patches = torch.empty((9 * N, C, Hp // 3, Wp // 3), device=dev, dtype=torch.float32)
+        ops.jigsaw_patchify(data.contiguous(), None, patches)
+        return_val = self.extract_features(patches)
+        feats = return_val["extracted_features"]                                 # [9N, C]
+        if jigsaw_orders is None:
+            jigsaw_orders = torch.stack([torch.randperm(9, device=dev) for _ in range(N)])   # vince_model.py:166
+        jigsaw_orders = jigsaw_orders.to(device=dev, dtype=torch.int64)
+        if shuffle_order is not None:
+            orders = torch.empty_like(jigsaw_orders)
+            orders[shuffle_order] = jigsaw_orders          # row i of the shuffled batch is original row shuffle_order[i]
+            jigsaw_orders = orders
+        head = self._heads["jigsaw"]
+        head.refresh()
+        feats = head.linear(0, feats, relu=False)                                # jigsaw_linear
+        gathered = torch.empty((N, 9 * feats.shape[1]), device=dev, dtype=torch.float32)
+        ops.jigsaw_gather(feats, jigsaw_orders.contiguous(), gathered)
+        hidden = head.linear(1, gathered, relu=True)
+        output = head.linear(2, hidden, relu=False)
+        self.launches += head.launches + 2
+        return_val["extracted_features"] = output                                # overwritten as in :172
+        return_val["prenorm_features"] = output
+        emb = torch.empty_like(output)
+        ops.l2_normalize(output, emb)
+        self.launches += 1
+        return_val["embeddings"] = emb
+        return return_val
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, inputs: Dict[str, torch.Tensor]):
+        """vince_model.py:198-250 (similarities) fused with loss_util.similarity_cross_entropy and get_metrics."""
+        return_val = copy.copy(inputs)
+        if inputs.get("data_source") == "IN":
+            raise NotImplementedError("ImageNet decoder branch (--use-imagenet) is outside the hot path")
+        output = return_val["embeddings"]
+        if "queue_embeddings" in inputs and "vince_similarities" not in inputs:
+            queue_embeddings = inputs["queue_embeddings"]
+            queue_vectors = inputs["queue_vectors"]
+            queue_tf32 = inputs.get("queue_vectors_tf32")
+            dev = output.device
+            ibc = bool(self.args.inter_batch_comparison)
+            nf = int(inputs["num_frames"]) if ibc else 0
+            with torch.no_grad(), torch.cuda.device(dev):
+                D = output.shape[1]
+                if D % 32 != 0 or D > 128:
+                    if D > 128:
+                        raise NotImplementedError("fused InfoNCE supports embedding sizes up to 128, got %d" % D)
+                    # odd embedding sizes (never used by the reference configs): zero-pad the feature dim,
+                    # which leaves every dot product unchanged
+                    Dp = (D + 31) // 32 * 32
+
+                    def pad(x):
+                        xp = torch.zeros((x.shape[0], Dp), device=dev, dtype=torch.float32)
+                        xp[:, :D] = x
+                        return xp
+                    output_k, queue_embeddings_k, queue_vectors_k = pad(output), pad(queue_embeddings), pad(queue_vectors)
+                    queue_tf32 = None
+                else:
+                    output_k, queue_embeddings_k, queue_vectors_k = output, queue_embeddings, queue_vectors
+                output_k, queue_embeddings_k = output_k.contiguous(), queue_embeddings_k.contiguous()
+                if queue_tf32 is None or queue_tf32.shape != queue_vectors_k.shape:
+                    queue_tf32 = torch.empty_like(queue_vectors_k)
+                    ops.round_tf32(queue_vectors_k.contiguous(), queue_tf32)
+                    self.launches += 1
+                fused = {"main": ops.infonce_fwd(output_k, queue_embeddings_k, queue_tf32, nf,
+                                                self.args.vince_temperature)}
+                self.launches += 4 if ibc else 3
+                if ibc and self.args.self_batch_comparison:
+                    fused["self"] = ops.infonce_fwd(output_k, output_k, None, nf, self.args.vince_self_temperature)
+                    self.launches += 4
+                    return_val["vince_self_similarities"] = LazySimilarity(output, [output])
+                    return_val["vince_self_similarities_mask"] = None
+            return_val["_vince_fused"] = fused
+            if ibc:
+                sims = LazySimilarity(output, [queue_embeddings, queue_vectors])
+                return_val["vince_l_neg"] = sims
+            else:
+                return_val["vince_l_neg"] = LazySimilarity(output, [queue_vectors])
+                return_val["vince_l_pos"] = fused["main"]["pos_sim"]
+                sims = LazySimilarity(output, [queue_vectors], prefix=fused["main"]["pos_sim"])
+            return_val["vince_similarities"] = sims
+            return_val["vince_similarities_mask"] = None      # positives are structural (block-diagonal); see _mask()
+        return return_val
+
+    def loss(self, network_outputs: Optional[Dict]) -> Dict[str, Optional[Tuple[float, torch.Tensor]]]:
+        if network_outputs is None:
+            losses = {"nce_loss": None}
+            if self.args.self_batch_comparison:
+                losses["nce_loss_self"] = None
+            return losses
+        losses = {}
+        if "_vince_fused" in network_outputs:
+            fused = network_outputs["_vince_fused"]
+            for key, name in (("main", ""), ("self", "self_")):
+                if key not in fused:
+                    continue
+                f = fused[key]
+                B, nP = f["dists"].shape
+                network_outputs.update({
+                    "vince_loss_" + name + "dists": f["dists"].view(B, 1, nP),
+                    "vince_loss_" + name + "dist": f["scalars"][0],
+                    "vince_loss_" + name + "softmax_weights": f["weights"].view(B, 1, nP),
+                    "vince_loss_" + name + "softmax_weight": f["scalars"][1],
+                })
+                losses["nce_loss" if key == "main" else "nce_loss_self"] = (1.0, f["scalars"][0])
+        elif "vince_similarities" in network_outputs:
+            # caller supplied an explicit similarity matrix: generic masked cross entropy kernel
+            similarities = network_outputs["vince_similarities"]
+            batch_size = similarities.shape[0]
+            mask = network_outputs["vince_similarities_mask"]
+            sl = loss_util.similarity_cross_entropy(similarities, self.args.vince_temperature, batch_size, 1, mask)
+            network_outputs.update({"vince_loss_" + key: val for key, val in sl.items()})
+            losses["nce_loss"] = (1.0, sl["dist"])
+            if self.args.self_batch_comparison:
+                sl = loss_util.similarity_cross_entropy(network_outputs["vince_self_similarities"],
+                                                        self.args.vince_self_temperature, batch_size, 1,
+                                                        network_outputs["vince_self_similarities_mask"])
+                network_outputs.update({"vince_loss_self_" + key: val for key, val in sl.items()})
+                losses["nce_loss_self"] = (1.0, sl["dist"])
+        return losses
+
+    def get_metrics(self, network_outputs: Optional[Dict]) -> Dict[str, Optional[float]]:
+        with torch.no_grad():
+            metrics = {}
+            if network_outputs is None:
+                metrics.update({"nce_accuracy_mean": None, "nce_softmax_weight_mean": None, "cosine_sim": None,
+                                "cosine_sim_neg_max": None})
+                if self.args.self_batch_comparison:
+                    metrics.update({"nce_accuracy_self_mean": None, "nce_softmax_weight_self_mean": None,
+                                    "cosine_self_sim": None})
+                return metrics
+            if "_vince_fused" in network_outputs:
+                fused = network_outputs["_vince_fused"]
+                for key, name in (("main", ""), ("self", "self_")):
+                    if key not in fused:
+                        continue
+                    sc = fused[key]["scalars"]
+                    metrics["nce_accuracy_" + name + "mean"] = sc[2]
+                    metrics["nce_softmax_weight_" + name + "mean"] = sc[1]
+                    metrics["cosine_" + name + "sim"] = sc[3]
+                    if key == "main":
+                        metrics["cosine_sim_neg_max"] = sc[4]
+            elif "vince_similarities" in network_outputs:
+                for key in ["", "self_"]:
+                    if "vince_" + key + "similarities" in network_outputs:
+                        m = loss_util.similarity_metrics(network_outputs["vince_" + key + "similarities"],
+                                                         network_outputs["vince_" + key + "similarities_mask"])
+                        metrics["nce_accuracy_" + key + "mean"] = m["nce_accuracy"]
+                        metrics["nce_softmax_weight_" + key + "mean"] = network_outputs["vince_loss_" + key + "softmax_weight"]
+                        metrics["cosine_" + key + "sim"] = m["cosine_sim"]
+                        if key == "":
+                            metrics["cosine_sim_neg_max"] = m["cosine_sim_neg_max"]
+            return metrics
+
+    def get_image_output(self, network_outputs) -> Dict[str, np.ndarray]:
+        # vince_model.py:351-571 builds tensorboard mosaics with cv2 on the CPU - visualisation, out of scope.
+        return {}
+
+
+class VinceQueueModel(BaseModel):
+    def __init__(self, args, encoder: VinceModel):
+        super(VinceQueueModel, self).__init__(args)
+        self.queue_network = copy.deepcopy(encoder)
+        self.vince_momentum = self.args.vince_momentum
+        for param in self.queue_network.parameters():
+            param.requires_grad = False
+        self._ema_table = None
+        self._ema_key = None
+        self.launches = 0
+
+    def to(self, device):
+        super(VinceQueueModel, self).to(device)
+        self.queue_network.to(device)
+        self._device = device
+
+    def _table(self, encoder_model):
+        import numpy as np
+        dst = self.queue_network.vince_parameters()
+        src = encoder_model.vince_parameters()
+        key = tuple(p.data_ptr() for p in dst) + tuple(p.data_ptr() for p in src)
+        if self._ema_key != key:
+            chunks = []
+            for d, s in zip(dst, src):
+                if d.shape != s.shape or d.dtype != torch.float32 or s.dtype != torch.float32:
+                    raise ValueError("param_update: parameter mismatch")
+                if not (d.is_cuda and s.is_cuda and d.device == s.device):
+                    raise RuntimeError("vince_b200 param_update: both encoders must live on the same CUDA device")
+                if not (d.is_contiguous() and s.is_contiguous()):
+                    raise ValueError("param_update: parameters must be contiguous")
+                n = d.numel()
+                for off in range(0, n, 8192):
+                    chunks.append((d.data_ptr() + 4 * off, s.data_ptr() + 4 * off, min(8192, n - off)))
+            arr = np.array(chunks, dtype=np.int64).reshape(-1, 3)
+            self._ema_table = (torch.from_numpy(arr.view(np.uint8).reshape(-1).copy()).to(dst[0].device), len(chunks))
+            self._ema_key = key
+        return self._ema_table
+
+    def param_update(self, encoder_model: VinceModel, momentum: float, enqueue=None):
+        """vince_model.py:587-592 as ONE launch.  `enqueue=(storage_queue, keys, images, data_source)` additionally
+        performs StorageQueue.enqueue in the same launch (the reference does it just before, vince_solver.py:497)."""
+        table, n = self._table(encoder_model)
+        dev = self.queue_network.vince_parameters()[0].device
+        with torch.no_grad(), torch.cuda.device(dev):
+            if enqueue is None:
+                ops.ema_enqueue(table, n, momentum)
+            else:
+                queue, keys, images, source = enqueue
+                if keys.shape[0] > queue.maxsize:
+                    raise ValueError("fused enqueue: batch larger than the queue")
+                tail = queue.current_tail
+                ops.ema_enqueue(table, n, momentum, queue.vector_queue, queue.vector_queue_tf32,
+                                keys.detach().contiguous(), tail)
+                queue.bookkeep(keys.shape[0], images, source)
+        self.launches = 1
+
+    def vince_update(self, encoder_model, enqueue=None):
+        self.param_update(encoder_model, self.vince_momentum, enqueue=enqueue)
+
+    def forward(self, inputs, jigsaw=False, shuffle=True, jigsaw_orders=None):
+        with torch.no_grad():
+            queue_data = inputs["queue_data"]
+            sub = {"data": queue_data}
+            if "batch_types" in inputs:
+                sub.update({"batch_types": inputs["batch_types"], "batch_sizes": inputs["batch_sizes"]})
+            output_mini_batches = self.queue_network.get_embeddings(sub, jigsaw=jigsaw, shuffle=shuffle,
+                                                                    jigsaw_orders=jigsaw_orders)
+            self.launches = self.queue_network.launches
+            single = isinstance(output_mini_batches, dict)
+            if single:
+                output_mini_batches = [output_mini_batches]
+            return_vals = []
+            for outputs in output_mini_batches:
+                return_val = {}
+                for key, val in outputs.items():
+                    if isinstance(val, torch.Tensor):
+                        val = val.detach()
+                    return_val["queue_" + key] = val
+                return_vals.append(return_val)
+            return return_vals
