@@ -39,11 +39,15 @@ int vince_abi_version(void);
 
 /* ---- convolution / linear layer as a tcgen05 implicit GEMM ------------------------------------------------
  * replaces: torchvision resnet conv2d calls reached from models/building_blocks/backbone_models.py:50-53
- *           (spec: models/building_blocks/resnet.py:76-92, 117-137, 231-247) and the nn.Linear layers of
- *           models/vince_model.py:38-49,163,171,177.
- * out[M,N] (fp32, row-major == NHWC) = epilogue(A * W^T); epilogue = optional per-channel scale, bias, ReLU;
+ *           (spec: models/building_blocks/resnet.py:76-92, 117-137, 231-247), the nn.Linear layers of
+ *           models/vince_model.py:38-49,163,171,177, and the statistics half of train-mode nn.BatchNorm2d.
+ * out[M,N] (fp32, row-major == NHWC) = epilogue(A * W^T); epilogue = optional per-channel scale, bias, ReLU.
  * `stats` (optional, [2][N] fp64, accumulated with +=) receives per-channel sum and sum of squares of the raw
- * outputs for train-mode BatchNorm (resnet.py:79,83 bn1/bn2 in training mode). */
+ * outputs.  When `bn_coef` is also given the kernel finishes train-mode BatchNorm itself (resnet.py:79,83 in
+ * training mode): the last CTA converts the sums into bn_coef[2][N] = (gamma/sqrt(var+eps), beta - mean*scale),
+ * updates running_mean / running_var (momentum, unbiased variance) and increments num_batches_tracked.
+ * 3x3 stride-1 pad-1 convolutions use a shared-memory halo path (one TMA load per tile serves all nine taps) when
+ * halo_mode = -1 (auto) finds it efficient, or always when halo_mode = 1; 0 forces the TMA-im2col path. */
 typedef struct {
   const void* a_hi;       /* bf16: [M,K] row-major, or NHWC [batch,H,W,Cin] when im2col != 0 */
   const void* a_lo;
@@ -58,10 +62,21 @@ typedef struct {
   const float* scale;
   const float* bias;
   int32_t relu;
-  int32_t reserved;
+  int32_t halo_mode;      /* -1 auto, 0 off, 1 force */
   double* stats;
+  const float* bn_gamma;
+  const float* bn_beta;
+  float* bn_running_mean;
+  float* bn_running_var;
+  int64_t* bn_num_batches_tracked;   /* may be NULL */
+  float* bn_coef;
+  uint32_t* bn_counter;   /* one zero-initialised word per launch */
+  float bn_momentum, bn_eps;
 } vince_conv_desc;
 int vince_conv_fwd(const vince_conv_desc* desc, void* stream);
+/* eval-mode BatchNorm coefficients from the running statistics: coef[2][C] */
+int vince_bn_eval_coef(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                       float eps, float* coef, int32_t C, void* stream);
 
 /* ---- stem input packing: NCHW fp32 -> X[n, j, q, 64] bf16 (hi, lo) ------------------------------------------
  * replaces: the input side of conv1 (7x7/2, pad 3; resnet.py:170,233) and the shuffle gather data[shuffle_order]
@@ -84,30 +99,24 @@ int vince_weight_prep(const vince_weight_entry* table_dev, int32_t n_entries, in
                       void* stream);
 
 /* ---- BatchNorm apply (+residual, +ReLU) and pooling ----------------------------------------------------------
- * replaces: nn.BatchNorm2d forward (train: batch statistics + running-stat update, momentum 0.1, unbiased var;
- *           eval: running statistics), the residual add and ReLU of resnet.py:76-92 / 117-137, MaxPool2d
- *           (resnet.py:173,236) and AdaptiveAvgPool2d (vince_model.py:33,128).
- * A `vince_bn_side` with stats == NULL means eval mode (running statistics, no update). */
+ * replaces: the normalisation half of nn.BatchNorm2d, the residual add and ReLU of resnet.py:76-92 / 117-137,
+ *           MaxPool2d (resnet.py:173,236) and AdaptiveAvgPool2d (vince_model.py:33,128).
+ * `coef` = [2][C] (scale, shift) from vince_conv_fwd's fused finalize (train) or vince_bn_eval_coef (eval). */
 typedef struct {
   const float* raw;       /* [M,C] raw conv output (NHWC) */
-  const double* stats;    /* [2][C] from vince_conv_fwd, or NULL */
-  const float* gamma;
-  const float* beta;
-  float* running_mean;
-  float* running_var;
-  int64_t* num_batches_tracked;
+  const float* coef;      /* [2][C] */
 } vince_bn_side;
 /* out = relu?( bn(main) + residual ); res_kind 0 none, 1 (res_hi,res_lo) planes, 2 bn(res_bn) (downsample branch) */
 int vince_bn_apply(const vince_bn_side* main, int32_t res_kind, const void* res_hi, const void* res_lo,
                    const vince_bn_side* res_bn, int32_t relu, void* out_hi, void* out_lo, float* out_f32, int64_t M,
-                   int32_t C, float momentum, float eps, void* stream);
+                   int32_t C, void* stream);
 int vince_bn_relu_maxpool(const vince_bn_side* bn, void* out_hi, void* out_lo, int32_t N, int32_t P, int32_t Q, int32_t C,
-                          float momentum, float eps, void* stream);
+                          void* stream);
 /* last block: relu(bn(main)+residual) -> spatial_features NCHW fp32 [N,C,h,w] + extracted_features [N,C]; output
  * row n is written at scatter_idx[n] (the un-shuffle of vince_model.py:184-192) */
 int vince_bn_final_pool(const vince_bn_side* main, int32_t res_kind, const void* res_hi, const void* res_lo,
                         const vince_bn_side* res_bn, const int64_t* scatter_idx, float* spatial_nchw, float* pooled,
-                        int32_t N, int32_t HW, int32_t C, float momentum, float eps, void* stream);
+                        int32_t N, int32_t HW, int32_t C, void* stream);
 
 /* ---- small helpers --------------------------------------------------------------------------------------------
  * vince_l2_normalize replaces F.normalize(dim=1) (vince_model.py:180); the jigsaw pair replaces

@@ -69,14 +69,23 @@ def check_gemm_tiled():
         w_hi, w_lo = split(w)
         out = torch.full((M, N), float("nan"), device=DEV)
         stats = torch.zeros((2, N), device=DEV, dtype=torch.float64)
+        bnm = _BN(N, g)
+        rm0, rv0 = bnm.running_mean.clone(), bnm.running_var.clone()
+        coef = torch.zeros((2 * N,), device=DEV)
+        counter = torch.zeros((2,), device=DEV, dtype=torch.int32)
         ops.conv_fwd(a_hi, a_lo if passes == 3 else None, w_hi, w_lo if passes == 3 else None, out, M, N, K,
-                     passes=passes, block_n=bn, stats=stats)
+                     passes=passes, block_n=bn, stats=stats.view(-1), bn=bnm, coef=coef, counter=counter)
         torch.cuda.synchronize()
         ref = a.double() @ w.double().t()
         tol = 3e-5 if passes == 3 else 1e-2
         report("gemm_tiled M%d N%d K%d p%d bn%d" % (M, N, K, passes, bn), rel(out, ref), tol)
         report("  stats sum", rel(stats[0], ref.sum(0)), 1e-4 if passes == 3 else 2e-2)
         report("  stats sumsq", rel(stats[1], (ref * ref).sum(0)), 1e-4 if passes == 3 else 2e-2)
+        if passes == 3:
+            sc_ref, sh_ref, rm_new, rv_new = bn_coef_ref(out, bnm, True, rm0, rv0)
+            report("  fused bn coef", rel(coef[:N], sc_ref) + rel(coef[N:], sh_ref), 1e-5)
+            report("  fused bn running", rel(bnm.running_mean, rm_new) + rel(bnm.running_var, rv_new), 1e-5,
+                   "nbt=%d" % int(bnm.num_batches_tracked))
     # bias + relu + scale epilogue
     M, N, K = 200, 128, 128
     a = torch.randn((M, K), generator=g).to(DEV)
@@ -92,7 +101,7 @@ def check_gemm_tiled():
     report("gemm_tiled scale+bias+relu", rel(out, ref), 3e-5)
 
 
-def conv_case(name, batch, H, W, Cin, Cout, R, stride, pad, passes=3, bn=0):
+def conv_case(name, batch, H, W, Cin, Cout, R, stride, pad, passes=3, bn=0, halo=0):
     g = torch.Generator().manual_seed(abs(hash(name)) % 1000)
     x = torch.randn((batch, Cin, H, W), generator=g).to(DEV)
     w = (torch.randn((Cout, Cin, R, R), generator=g) * (2.0 / (Cin * R * R)) ** 0.5).to(DEV)
@@ -107,7 +116,7 @@ def conv_case(name, batch, H, W, Cin, Cout, R, stride, pad, passes=3, bn=0):
     geom = dict(batch=batch, H=H, W=W, Cin=Cin, R=R, S=R, stride=stride, pad_lo_h=pad, pad_lo_w=pad, pad_hi_h=pad,
                 pad_hi_w=pad)
     ops.conv_fwd(a_hi, a_lo if passes == 3 else None, w_hi, w_lo if passes == 3 else None, out, M, Cout, R * R * Cin,
-                 passes=passes, geom=geom, block_n=bn, stats=stats)
+                 passes=passes, geom=geom, block_n=bn, stats=stats.view(-1), halo_mode=halo)
     torch.cuda.synchronize()
     ref = F.conv2d(x.double(), w.double(), stride=stride, padding=pad).permute(0, 2, 3, 1).reshape(M, Cout)
     e = rel(out, ref)
@@ -130,6 +139,18 @@ def check_conv_im2col():
     conv_case("conv1x1 s1 as im2col 9x9 128->64", 2, 9, 9, 128, 64, 1, 1, 0)
     conv_case("conv3x3 s1 bf16x1", 2, 14, 14, 64, 64, 3, 1, 1, passes=1)
     conv_case("conv3x3 s1 14x14 256->256 bn256", 4, 14, 14, 256, 256, 3, 1, 1, bn=256)
+
+
+def check_conv_halo():
+    conv_case("halo 56x56 64->64 b3", 3, 56, 56, 64, 64, 3, 1, 1, halo=1)
+    conv_case("halo 28x28 128->128 b5", 5, 28, 28, 128, 128, 3, 1, 1, halo=1)
+    conv_case("halo 14x14 256->256 b4", 4, 14, 14, 256, 256, 3, 1, 1, halo=1)
+    conv_case("halo 7x7 512->512 b4", 4, 7, 7, 512, 512, 3, 1, 1, halo=1)
+    conv_case("halo 15x13 64->128 (odd)", 3, 15, 13, 64, 128, 3, 1, 1, halo=1)
+    conv_case("halo 19x19 128->64 b2", 2, 19, 19, 128, 64, 3, 1, 1, halo=1)
+    conv_case("halo 8x126 64->64 b2 (Wp=128)", 2, 8, 126, 64, 64, 3, 1, 1, halo=1)
+    conv_case("halo 56x56 bf16x1", 2, 56, 56, 64, 64, 3, 1, 1, passes=1, halo=1)
+    conv_case("halo auto 56x56 64->64 b16", 16, 56, 56, 64, 64, 3, 1, 1, halo=-1)
 
 
 def check_stem():
@@ -162,6 +183,26 @@ class _BN:
         self.num_batches_tracked = torch.zeros((), dtype=torch.int64, device=DEV)
 
 
+def bn_coef_ref(raw, bn, train, rm, rv):
+    """fp64 reference of (scale, shift, new running mean, new running var)"""
+    raw = raw.double()
+    if train:
+        mean, var = raw.mean(0), raw.var(0, unbiased=False)
+        n = raw.shape[0]
+        rm_new = 0.9 * rm.double() + 0.1 * mean
+        rv_new = 0.9 * rv.double() + 0.1 * var * n / (n - 1)
+    else:
+        mean, var, rm_new, rv_new = rm.double(), rv.double(), rm.double(), rv.double()
+    sc = bn.weight.double() / torch.sqrt(var + 1e-5)
+    return sc, bn.bias.double() - mean * sc, rm_new, rv_new
+
+
+def make_coef(raw, bn, train):
+    """coef tensor as the kernels expect it ([scale | shift], fp32), computed in torch for the apply-only checks"""
+    sc, sh, _, _ = bn_coef_ref(raw, bn, train, bn.running_mean, bn.running_var)
+    return torch.cat((sc, sh)).float().contiguous()
+
+
 def bn_ref(raw, bn, train, rm, rv):
     raw = raw.double()
     if train:
@@ -185,10 +226,7 @@ def check_bn_apply():
         for train in (True, False):
             for res_kind in (0, 1, 2):
                 bn, bn2 = _BN(C, g), _BN(C, g)
-                rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
-                rm20, rv20 = bn2.running_mean.clone(), bn2.running_var.clone()
-                stats = torch.stack([raw.double().sum(0), (raw.double() ** 2).sum(0)]) if train else None
-                stats2 = torch.stack([raw2.double().sum(0), (raw2.double() ** 2).sum(0)]) if train else None
+                coef, coef2 = make_coef(raw, bn, train), make_coef(raw2, bn2, train)
                 out_hi = torch.empty((M, C), device=DEV, dtype=torch.bfloat16)
                 out_lo = torch.empty_like(out_hi)
                 out_f = torch.empty((M, C), device=DEV)
@@ -197,22 +235,26 @@ def check_bn_apply():
                 if res_kind == 1:
                     kw["res_planes"] = (r_hi, r_lo)
                 elif res_kind == 2:
-                    kw["res_bn"] = ops.bn_side(raw2, stats2, bn2)
-                ops.bn_apply(ops.bn_side(raw, stats, bn), M, C, True, out_hi, out_lo, out_f, **kw)
+                    kw["res_bn"] = ops.bn_side(raw2, coef2)
+                ops.bn_apply(ops.bn_side(raw, coef), M, C, True, out_hi, out_lo, out_f, **kw)
                 torch.cuda.synchronize()
-                y, rm_new, rv_new = bn_ref(raw, bn, train, rm0, rv0)
+                y, _, _ = bn_ref(raw, bn, train, bn.running_mean, bn.running_var)
                 if res_kind == 1:
                     y = y + (r_hi.double() + r_lo.double())
                 elif res_kind == 2:
-                    y2, rm2_new, rv2_new = bn_ref(raw2, bn2, train, rm20, rv20)
+                    y2, _, _ = bn_ref(raw2, bn2, train, bn2.running_mean, bn2.running_var)
                     y = y + y2
                 y = F.relu(y)
                 tag = "bn_apply C%d %s res%d" % (C, "train" if train else "eval", res_kind)
                 report(tag + " f32", rel(out_f, y), 2e-6)
                 report(tag + " hi+lo", rel(out_hi.double() + out_lo.double(), y), 2e-5)
-                report(tag + " running", rel(bn.running_mean, rm_new) + rel(bn.running_var, rv_new), 1e-6)
-                if train:
-                    report(tag + " nbt", abs(int(bn.num_batches_tracked) - 1), 0)
+        # eval-mode coefficient kernel
+        bn = _BN(C, g)
+        coef = torch.zeros((2 * C,), device=DEV)
+        ops.build_bn_eval_coef(bn, coef)()
+        torch.cuda.synchronize()
+        sc, sh, _, _ = bn_coef_ref(raw, bn, False, bn.running_mean, bn.running_var)
+        report("bn_eval_coef C%d" % C, rel(coef[:C], sc) + rel(coef[C:], sh), 1e-6)
 
 
 def check_maxpool_finalpool():
@@ -220,18 +262,26 @@ def check_maxpool_finalpool():
     N, P, Q, C = 3, 16, 12, 64
     raw = torch.randn((N, P, Q, C), generator=g).to(DEV)
     bn = _BN(C, g)
-    rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
     flat = raw.reshape(-1, C)
-    stats = torch.stack([flat.double().sum(0), (flat.double() ** 2).sum(0)])
     P2, Q2 = (P - 1) // 2 + 1, (Q - 1) // 2 + 1
     out_hi = torch.empty((N, P2, Q2, C), device=DEV, dtype=torch.bfloat16)
     out_lo = torch.empty_like(out_hi)
-    ops.bn_relu_maxpool(ops.bn_side(raw, stats, bn), out_hi, out_lo, N, P, Q, C)
+    ops.bn_relu_maxpool(ops.bn_side(raw, make_coef(flat, bn, True)), out_hi, out_lo, N, P, Q, C)
     torch.cuda.synchronize()
-    y, _, _ = bn_ref(flat, bn, True, rm0, rv0)
+    y, _, _ = bn_ref(flat, bn, True, bn.running_mean, bn.running_var)
     y = F.relu(y).reshape(N, P, Q, C).permute(0, 3, 1, 2)
     ref = F.max_pool2d(y, 3, 2, 1).permute(0, 2, 3, 1)
     report("bn_relu_maxpool", rel(out_hi.double() + out_lo.double(), ref), 2e-5)
+    N, P, Q, C = 2, 112, 112, 64
+    raw = torch.randn((N, P, Q, C), generator=g).to(DEV)
+    flat = raw.reshape(-1, C)
+    out_hi = torch.empty((N, 56, 56, C), device=DEV, dtype=torch.bfloat16)
+    out_lo = torch.empty_like(out_hi)
+    ops.bn_relu_maxpool(ops.bn_side(raw, make_coef(flat, bn, True)), out_hi, out_lo, N, P, Q, C)
+    torch.cuda.synchronize()
+    y, _, _ = bn_ref(flat, bn, True, bn.running_mean, bn.running_var)
+    ref = F.max_pool2d(F.relu(y).reshape(N, P, Q, C).permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    report("bn_relu_maxpool 112x112", rel(out_hi.double() + out_lo.double(), ref), 2e-5)
     # final pool
     for C in (512, 2048):
         N, HW = 5, 49
@@ -239,14 +289,13 @@ def check_maxpool_finalpool():
         res = torch.randn((N * HW, C), generator=g).to(DEV)
         r_hi, r_lo = split(res)
         bn = _BN(C, g)
-        rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
-        stats = torch.stack([raw.double().sum(0), (raw.double() ** 2).sum(0)])
         perm = torch.randperm(N, generator=g).to(DEV)
         spatial = torch.empty((N, C, 7, 7), device=DEV)
         pooled = torch.empty((N, C), device=DEV)
-        ops.bn_final_pool(ops.bn_side(raw, stats, bn), N, HW, C, spatial, pooled, scatter_idx=perm, res_planes=(r_hi, r_lo))
+        ops.bn_final_pool(ops.bn_side(raw, make_coef(raw, bn, True)), N, HW, C, spatial, pooled, scatter_idx=perm,
+                          res_planes=(r_hi, r_lo))
         torch.cuda.synchronize()
-        y, _, _ = bn_ref(raw, bn, True, rm0, rv0)
+        y, _, _ = bn_ref(raw, bn, True, bn.running_mean, bn.running_var)
         y = F.relu(y + r_hi.double() + r_lo.double()).reshape(N, HW, C).permute(0, 2, 1).reshape(N, C, 7, 7)
         ref_sp = torch.empty_like(y)
         ref_sp[perm] = y
@@ -360,7 +409,7 @@ def check_infonce():
 
 
 CHECKS = [check_small, check_ema_enqueue, check_bn_apply, check_maxpool_finalpool, check_gemm_tiled, check_conv_im2col,
-          check_stem, check_infonce]
+          check_conv_halo, check_stem, check_infonce]
 
 
 def main():

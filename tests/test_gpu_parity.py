@@ -386,7 +386,11 @@ def test_encoder_full_batch_eval_is_batch_separable():
     b = model.get_embeddings({"data": x[128:].contiguous()})["embeddings"]
     torch.cuda.synchronize()
     assert torch.isfinite(full).all()
-    assert rel(full, torch.cat((a, b))) < 1e-6
+    # not bit-exact: the tile-width / halo-vs-im2col choice depends on the batch, which changes the fp32 summation
+    # order inside a convolution (channel-block-major vs tap-major); 1e-5 is ~2 orders below the parity tolerance
+    err = rel(full, torch.cat((a, b)))
+    print("full-batch vs two halves, eval mode: rel-L2 %.2e" % err)
+    assert err < 1e-5
     assert rel(full.norm(dim=1), torch.ones(256)) < 1e-6
 
 

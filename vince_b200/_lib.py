@@ -8,7 +8,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libvince_b200.so")
+LIB_PATH = os.environ.get("VINCE_B200_LIB", os.path.join(_HERE, "csrc", "libvince_b200.so"))
 
 
 class ConvDesc(Structure):
@@ -18,15 +18,15 @@ class ConvDesc(Structure):
         ("batch", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("R", c_int32), ("S", c_int32),
         ("stride", c_int32), ("pad_lo_h", c_int32), ("pad_lo_w", c_int32), ("pad_hi_h", c_int32),
         ("pad_hi_w", c_int32), ("passes", c_int32), ("block_n", c_int32),
-        ("scale", c_void_p), ("bias", c_void_p), ("relu", c_int32), ("reserved", c_int32), ("stats", c_void_p),
+        ("scale", c_void_p), ("bias", c_void_p), ("relu", c_int32), ("halo_mode", c_int32), ("stats", c_void_p),
+        ("bn_gamma", c_void_p), ("bn_beta", c_void_p), ("bn_running_mean", c_void_p), ("bn_running_var", c_void_p),
+        ("bn_num_batches_tracked", c_void_p), ("bn_coef", c_void_p), ("bn_counter", c_void_p),
+        ("bn_momentum", c_float), ("bn_eps", c_float),
     ]
 
 
 class BnSide(Structure):
-    _fields_ = [
-        ("raw", c_void_p), ("stats", c_void_p), ("gamma", c_void_p), ("beta", c_void_p),
-        ("running_mean", c_void_p), ("running_var", c_void_p), ("num_batches_tracked", c_void_p),
-    ]
+    _fields_ = [("raw", c_void_p), ("coef", c_void_p)]
 
 
 class InfoNceDesc(Structure):
@@ -46,12 +46,13 @@ SIGNATURES = {
     "vince_conv_fwd": (c_int32, [POINTER(ConvDesc), c_void_p]),
     "vince_stem_pack": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "vince_weight_prep": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
+    "vince_bn_eval_coef": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int32, c_void_p]),
     "vince_bn_apply": (c_int32, [POINTER(BnSide), c_int32, c_void_p, c_void_p, POINTER(BnSide), c_int32, c_void_p,
-                                 c_void_p, c_void_p, c_int64, c_int32, c_float, c_float, c_void_p]),
+                                 c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "vince_bn_relu_maxpool": (c_int32, [POINTER(BnSide), c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
-                                        c_float, c_float, c_void_p]),
+                                        c_void_p]),
     "vince_bn_final_pool": (c_int32, [POINTER(BnSide), c_int32, c_void_p, c_void_p, POINTER(BnSide), c_void_p,
-                                      c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_void_p]),
+                                      c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "vince_split_bf16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "vince_round_tf32": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
     "vince_l2_normalize": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),

@@ -2,6 +2,7 @@
 // the internal descriptors, launches.  NCCL is bound at run time with dlopen so the library loads (and exports
 // every symbol) on machines without NCCL or a GPU.
 #include <dlfcn.h>
+#include <stdlib.h>
 
 #include "../../include/vince_b200.h"
 #include "common.cuh"
@@ -16,16 +17,13 @@ static inline const __nv_bfloat16* BF(const void* p) { return reinterpret_cast<c
 static BnSide to_side(const vince_bn_side* s) {
   BnSide o;
   memset(&o, 0, sizeof(o));
-  if (s) {
-    o.raw = s->raw, o.stats = s->stats, o.gamma = s->gamma, o.beta = s->beta;
-    o.running_mean = s->running_mean, o.running_var = s->running_var, o.num_batches_tracked = s->num_batches_tracked;
-  }
+  if (s) o.raw = s->raw, o.coef = s->coef;
   return o;
 }
 
 static int check_side(const vince_bn_side* s, const char* what) {
   VB_REQUIRE(s != nullptr, "%s: null bn side", what);
-  VB_REQUIRE(s->raw && s->gamma && s->beta && s->running_mean && s->running_var, "%s: null pointer in bn side", what);
+  VB_REQUIRE(s->raw && s->coef, "%s: null pointer in bn side", what);
   return VB_OK;
 }
 
@@ -44,7 +42,18 @@ int vince_conv_fwd(const vince_conv_desc* d, void* stream) {
   g.pad_lo_h = d->pad_lo_h, g.pad_lo_w = d->pad_lo_w, g.pad_hi_h = d->pad_hi_h, g.pad_hi_w = d->pad_hi_w;
   g.passes = d->passes, g.block_n = d->block_n, g.scale = d->scale, g.bias = d->bias, g.relu = d->relu;
   g.stats = d->stats;
+  g.halo_mode = d->halo_mode;
+  g.bn_gamma = d->bn_gamma, g.bn_beta = d->bn_beta, g.bn_running_mean = d->bn_running_mean;
+  g.bn_running_var = d->bn_running_var, g.bn_num_batches_tracked = d->bn_num_batches_tracked;
+  g.bn_coef = d->bn_coef, g.bn_counter = d->bn_counter, g.bn_momentum = d->bn_momentum, g.bn_eps = d->bn_eps;
+  g.trace = getenv("VINCE_B200_TRACE_PTR") ? reinterpret_cast<void*>(strtoull(getenv("VINCE_B200_TRACE_PTR"), nullptr, 0)) : nullptr;
   return conv_gemm_launch(g, S(stream));
+}
+
+int vince_bn_eval_coef(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                       float eps, float* coef, int32_t C, void* stream) {
+  VB_REQUIRE(C == 0 || (gamma && beta && running_mean && running_var && coef), "vince_bn_eval_coef: null pointer");
+  return bn_eval_coef_launch(gamma, beta, running_mean, running_var, eps, coef, C, S(stream));
 }
 
 int vince_stem_pack(const float* x, const int64_t* gather_idx, void* x_hi, void* x_lo, int32_t N, int32_t H, int32_t W,
@@ -64,7 +73,7 @@ int vince_weight_prep(const vince_weight_entry* table_dev, int32_t n_entries, in
 
 int vince_bn_apply(const vince_bn_side* main, int32_t res_kind, const void* res_hi, const void* res_lo,
                    const vince_bn_side* res_bn, int32_t relu, void* out_hi, void* out_lo, float* out_f32, int64_t M,
-                   int32_t C, float momentum, float eps, void* stream) {
+                   int32_t C, void* stream) {
   int rc = check_side(main, "vince_bn_apply");
   if (rc) return rc;
   VB_REQUIRE(res_kind >= 0 && res_kind <= 2, "vince_bn_apply: res_kind %d", res_kind);
@@ -72,21 +81,21 @@ int vince_bn_apply(const vince_bn_side* main, int32_t res_kind, const void* res_
   if (res_kind == 2 && (rc = check_side(res_bn, "vince_bn_apply(residual)"))) return rc;
   VB_REQUIRE(out_hi || out_f32, "vince_bn_apply: no output");
   return bn_apply_launch(to_side(main), res_kind, BF(res_hi), BF(res_lo), to_side(res_bn), relu, BF(out_hi), BF(out_lo),
-                         out_f32, M, C, momentum, eps, S(stream));
+                         out_f32, M, C, S(stream));
 }
 
 int vince_bn_relu_maxpool(const vince_bn_side* bn, void* out_hi, void* out_lo, int32_t N, int32_t P, int32_t Q, int32_t C,
-                          float momentum, float eps, void* stream) {
+                          void* stream) {
   int rc = check_side(bn, "vince_bn_relu_maxpool");
   if (rc) return rc;
   VB_REQUIRE(out_hi, "vince_bn_relu_maxpool: null output");
   const int P2 = (P + 2 - 3) / 2 + 1, Q2 = (Q + 2 - 3) / 2 + 1;
-  return bn_relu_maxpool_launch(to_side(bn), BF(out_hi), BF(out_lo), N, P, Q, C, P2, Q2, momentum, eps, S(stream));
+  return bn_relu_maxpool_launch(to_side(bn), BF(out_hi), BF(out_lo), N, P, Q, C, P2, Q2, S(stream));
 }
 
 int vince_bn_final_pool(const vince_bn_side* main, int32_t res_kind, const void* res_hi, const void* res_lo,
                         const vince_bn_side* res_bn, const int64_t* scatter_idx, float* spatial_nchw, float* pooled,
-                        int32_t N, int32_t HW, int32_t C, float momentum, float eps, void* stream) {
+                        int32_t N, int32_t HW, int32_t C, void* stream) {
   int rc = check_side(main, "vince_bn_final_pool");
   if (rc) return rc;
   VB_REQUIRE(res_kind >= 0 && res_kind <= 2, "vince_bn_final_pool: res_kind %d", res_kind);
@@ -94,7 +103,7 @@ int vince_bn_final_pool(const vince_bn_side* main, int32_t res_kind, const void*
   if (res_kind == 2 && (rc = check_side(res_bn, "vince_bn_final_pool(residual)"))) return rc;
   VB_REQUIRE(pooled, "vince_bn_final_pool: pooled output null");
   return bn_final_pool_launch(to_side(main), res_kind, BF(res_hi), BF(res_lo), to_side(res_bn), scatter_idx,
-                              spatial_nchw, pooled, N, HW, C, momentum, eps, S(stream));
+                              spatial_nchw, pooled, N, HW, C, S(stream));
 }
 
 int vince_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream) {

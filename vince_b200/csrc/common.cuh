@@ -48,6 +48,10 @@ int encode_tma_im2col_nhwc(CUtensorMap* map, CUtensorMapDataType dtype, const vo
                            int pad_lo_h, int pad_lo_w, int pad_hi_h, int pad_hi_w, int R, int S, int stride,
                            uint32_t channels_per_pixel, uint32_t pixels_per_column, CUtensorMapSwizzle swz);
 
+// NHWC tensor [N,H,W,C] as a 4-D tiled map with box {box_c, box_w, box_h, 1} (halo loads / NHWC tile stores)
+int encode_tma_4d_nhwc(CUtensorMap* map, CUtensorMapDataType dtype, const void* base, int N, int H, int W, int C,
+                       uint32_t box_c, uint32_t box_w, uint32_t box_h, CUtensorMapSwizzle swz);
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------
 // device-side PTX wrappers

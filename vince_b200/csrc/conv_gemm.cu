@@ -2,42 +2,92 @@
 //
 //   out[M, N] = epilogue( A[M, K] * W[N, K]^T )         fp32 accumulate in TMEM
 //
-// * A is either a plain row-major [M, K] matrix (1x1 stride-1 convs, Linear layers; 2-D tiled TMA) or an
-//   NHWC activation tensor gathered on the fly by TMA *im2col* loads (KxK / strided convs): k-block kb
-//   maps to filter tap (r, s) = (kb / cin_blocks) and input-channel block (kb % cin_blocks).
-// * Operands are bf16.  To reproduce the reference's fp32 arithmetic (torch conv2d / mm, SURVEY.md 7
-//   "hard parts") every fp32 value is carried as a bf16 (hi, lo) pair and each k-step issues three MMAs
-//   hi*hi + lo*hi + hi*lo into the same accumulator ("bf16x3", passes = 3).  passes = 1 is plain bf16.
-// * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-//   warps 2..5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store; per-channel sum / sum-of-squares
-//   for train-mode BatchNorm accumulated in fp64).  Accumulators are double-buffered in TMEM so the epilogue
-//   of tile t overlaps the main loop of tile t+1.  One CTA per SM; tiles are handed out round-robin with the
-//   M index fastest so that concurrently running CTAs share the weight tile through L2.
+// A-operand modes
+//   0 TILED   A is a plain row-major [M, K] matrix (1x1 stride-1 convs, Linear layers): 2-D tiled TMA.
+//   1 IM2COL  NHWC activation gathered on the fly by TMA *im2col* loads (strided / 7x7-stem / small-map convs):
+//             k-block kb = filter tap (r, s) x 64-channel block.
+//   2 HALO    3x3 stride-1 pad-1 convs on larger maps: a tile is TH full image rows; ONE tiled 4-D TMA load brings the
+//             (TH+2) x (W+2) x 64ch input halo (zero-filled outside the image) into shared memory and all nine
+//             filter taps read it through row-shifted UMMA descriptors (start address + (r*(W+2)+s)*128 B), cutting
+//             the L2->SM activation traffic ~4.7x versus im2col.  Positions x >= W of each padded row are computed
+//             and discarded.
+// Operands are bf16.  To reproduce the reference's fp32 arithmetic (torch conv2d / mm, SURVEY.md 7 "hard parts") every
+// fp32 value is carried as a bf16 (hi, lo) pair and each k-step issues three MMAs lo*hi + hi*lo + hi*hi into the same
+// accumulator ("bf16x3", passes = 3).  passes = 1 is plain bf16.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (separate A and B rings), warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store; per-channel sum / sum-of-squares for
+// train-mode BatchNorm accumulated in fp64; the LAST CTA to finish turns the sums into per-channel scale/shift and
+// updates the running statistics, so no separate BN-finalize launch exists).  Accumulators are double-buffered in
+// TMEM so the epilogue of tile t overlaps the main loop of tile t+1.  One CTA per SM; tiles are handed out round-robin
+// with the M index fastest so that concurrently running CTAs share the weight tile through L2.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace vb {
 
-constexpr int BM = 128;          // rows (output pixels) per tile  == UMMA M == TMEM lanes
-constexpr int BK = 64;           // bf16 elements per k-block       == one 128-byte swizzle row
+constexpr int BM = 128;          // rows (output positions) per tile == UMMA M == TMEM lanes
+constexpr int BK = 64;           // bf16 elements per k-block        == one 128-byte swizzle row
 constexpr int UMMA_K = 16;       // bf16
 constexpr int GEMM_THREADS = 192;
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_RING = 8;
 constexpr int STAGING_BYTES = BM * 128;   // 128 rows x 32 fp32
 
 struct GemmKernelParams {
   CUtensorMap a_hi, a_lo, b_hi, b_lo, out;
   int M, N;
-  int num_m_blocks, num_n_blocks, num_k_blocks;
-  int a_mode;                    // 0 tiled [M,K]; 1 im2col NHWC
-  int PQ, Q, stride, pad_h, pad_w, S, cin_blocks;
-  int passes;                    // 1 or 3
-  int num_stages;
-  const float* scale;            // optional per-channel multiplier
-  const float* bias;             // optional per-channel addend
+  int num_m_blocks, num_n_blocks;
+  int a_mode;                    // 0 tiled, 1 im2col, 2 halo
+  int a_chunks;                  // A loads per tile (modes 0/1: k-blocks; halo: 64-channel blocks)
+  int b_per_a;                   // B loads (k-blocks) per A load (modes 0/1: 1; halo: 9 taps)
+  int PQ, Q, stride, pad_h, pad_w, S, cin_blocks;        // im2col geometry
+  int Wp, TH, tiles_per_img, H, W;                        // halo geometry
+  uint32_t a_plane_bytes;        // smem bytes reserved per A plane per stage (multiple of 1024)
+  uint32_t a_tx_bytes;           // bytes one A-plane TMA load delivers
+  int passes;
+  int a_stages, b_stages;
+  const float* scale;
+  const float* bias;
   int relu;
-  double* stats;                 // optional [2][N]: sum, sum of squares over rows (raw accumulators)
+  double* stats;                 // optional [2][N]
+  // train-mode BatchNorm finalize by the last CTA (all optional; need stats)
+  const float* bn_gamma;
+  const float* bn_beta;
+  float* bn_running_mean;
+  float* bn_running_var;
+  long long* bn_nbt;
+  float* bn_coef;                // [2][N]: scale, shift
+  unsigned int* bn_counter;
+  float bn_momentum, bn_eps;
+  double bn_count;
+  unsigned long long* trace;     // debug timeline (VB_TRACE builds only): [4 tags][512] clock64 stamps of CTA 0
 };
+
+#ifdef VB_TRACE
+#define VB_TRACE_EVENT(tag, idx)                                                              \
+  do {                                                                                        \
+    if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 512) p.trace[(tag) * 512 + (idx)] = clock64(); \
+  } while (0)
+#else
+#define VB_TRACE_EVENT(tag, idx) \
+  do {                           \
+  } while (0)
+#endif
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0,
+                                            int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int32_t c0, int32_t c1,
+                                             int32_t c2, int32_t c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
@@ -48,18 +98,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int planes = (p.passes == 3) ? 2 : 1;
-  constexpr uint32_t A_TILE = BM * 128;            // bytes per plane
   constexpr uint32_t B_TILE = BN * 128;
-  const uint32_t stage_bytes = (A_TILE + B_TILE) * planes;
+  const uint32_t a_stage_bytes = p.a_plane_bytes * planes;
+  const uint32_t b_stage_bytes = B_TILE * planes;
 
-  uint8_t* stages = smem;
-  uint8_t* staging = smem + (size_t)p.num_stages * stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
-  uint64_t* empty_bar = full_bar + MAX_STAGES;
-  uint64_t* tmem_full = empty_bar + MAX_STAGES;
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = a_ring + (size_t)p.a_stages * a_stage_bytes;
+  uint8_t* staging = b_ring + (size_t)p.b_stages * b_stage_bytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
+  uint64_t* a_empty = a_full + MAX_RING;
+  uint64_t* b_full = a_empty + MAX_RING;
+  uint64_t* b_empty = b_full + MAX_RING;
+  uint64_t* tmem_full = b_empty + MAX_RING;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  double* smem_stats = reinterpret_cast<double*>(tmem_ptr + 2);     // [2][BN]
+  uint32_t* last_flag = tmem_ptr + 1;
+  double* smem_stats = reinterpret_cast<double*>(tmem_ptr + 2);     // [4 epilogue warps][2][BN], warp-private
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a_hi);
@@ -69,9 +123,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       tma_prefetch_desc(&p.a_lo);
       tma_prefetch_desc(&p.b_lo);
     }
-    for (int s = 0; s < p.num_stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < p.a_stages; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < p.b_stages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -84,7 +142,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     tmem_relinquish();
   }
   if (threadIdx.x >= 64) {
-    for (int i = threadIdx.x - 64; i < 2 * BN; i += 128) smem_stats[i] = 0.0;
+    for (int i = threadIdx.x - 64; i < 8 * BN; i += 128) smem_stats[i] = 0.0;
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -93,104 +151,157 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
 
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
 
+  // The producer and MMA warps keep their control flow WARP-UNIFORM (all 32 lanes walk the loops and wait on the
+  // barriers) and elect one lane only around the TMA / tcgen05 instructions themselves: tile indices, stage
+  // counters, smem addresses and descriptors then live in uniform registers, which is what UTMALDG / UTCHMMA
+  // consume.  Running the whole loop under `if (lane == 0)` makes ptxas treat every operand as divergent and
+  // emit a waterfall of R2UR moves per instruction (~90 cycles per MMA issue, measured).
   if (warp == 0) {
     // ======================= TMA producer =======================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % p.num_m_blocks;
-        const int n_blk = tile / p.num_m_blocks;
-        const int m0 = m_blk * BM;
-        int img = 0, ph = 0, qw = 0;
+    int as = 0, bs = 0;
+    uint32_t aphase = 0, bphase = 0;
+    int tr_p = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.num_m_blocks;
+      const int n_blk = tile / p.num_m_blocks;
+      const int m0 = m_blk * BM;
+      int img = 0, ph = 0, qw = 0;
+      if (p.a_mode == 1) {
+        img = m0 / p.PQ;
+        const int rem = m0 - img * p.PQ;
+        const int p0 = rem / p.Q;
+        const int q0 = rem - p0 * p.Q;
+        ph = p0 * p.stride - p.pad_h;
+        qw = q0 * p.stride - p.pad_w;
+      } else if (p.a_mode == 2) {
+        img = m_blk / p.tiles_per_img;
+        ph = (m_blk - img * p.tiles_per_img) * p.TH - 1;        // first halo row
+      }
+      for (int ac = 0; ac < p.a_chunks; ++ac) {
+        mbar_wait(&a_empty[as], aphase ^ 1);
+        uint8_t* a_hi = a_ring + (size_t)as * a_stage_bytes;
+        uint8_t* a_lo = a_hi + p.a_plane_bytes;
+        int tap = 0, cb = 0, r = 0, sx = 0;
         if (p.a_mode == 1) {
-          img = m0 / p.PQ;
-          const int rem = m0 - img * p.PQ;
-          const int p0 = rem / p.Q;
-          const int q0 = rem - p0 * p.Q;
-          ph = p0 * p.stride - p.pad_h;
-          qw = q0 * p.stride - p.pad_w;
+          tap = ac / p.cin_blocks;
+          cb = ac - tap * p.cin_blocks;
+          r = tap / p.S;
+          sx = tap - r * p.S;
         }
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* st = stages + (size_t)stage * stage_bytes;
-          uint8_t* a_hi = st;
-          uint8_t* a_lo = st + A_TILE;
-          uint8_t* b_hi = st + A_TILE * planes;
-          uint8_t* b_lo = b_hi + B_TILE;
-          mbar_expect_tx(&full_bar[stage], stage_bytes);
+        if (elect_one()) {
+          mbar_expect_tx(&a_full[as], p.a_tx_bytes * planes);
           if (p.a_mode == 0) {
-            tma_load_2d(a_hi, &p.a_hi, &full_bar[stage], kb * BK, m0);
-            if (planes == 2) tma_load_2d(a_lo, &p.a_lo, &full_bar[stage], kb * BK, m0);
-          } else {
-            const int tap = kb / p.cin_blocks;
-            const int cb = kb - tap * p.cin_blocks;
-            const int r = tap / p.S;
-            const int s = tap - r * p.S;
-            tma_load_im2col_4d(a_hi, &p.a_hi, &full_bar[stage], cb * BK, qw, ph, img, (uint16_t)s, (uint16_t)r);
+            tma_load_2d(a_hi, &p.a_hi, &a_full[as], ac * BK, m0);
+            if (planes == 2) tma_load_2d(a_lo, &p.a_lo, &a_full[as], ac * BK, m0);
+          } else if (p.a_mode == 1) {
+            tma_load_im2col_4d(a_hi, &p.a_hi, &a_full[as], cb * BK, qw, ph, img, (uint16_t)sx, (uint16_t)r);
             if (planes == 2)
-              tma_load_im2col_4d(a_lo, &p.a_lo, &full_bar[stage], cb * BK, qw, ph, img, (uint16_t)s, (uint16_t)r);
+              tma_load_im2col_4d(a_lo, &p.a_lo, &a_full[as], cb * BK, qw, ph, img, (uint16_t)sx, (uint16_t)r);
+          } else {
+            tma_load_4d(a_hi, &p.a_hi, &a_full[as], ac * BK, -1, ph, img);
+            if (planes == 2) tma_load_4d(a_lo, &p.a_lo, &a_full[as], ac * BK, -1, ph, img);
           }
-          tma_load_2d(b_hi, &p.b_hi, &full_bar[stage], kb * BK, n_blk * BN);
-          if (planes == 2) tma_load_2d(b_lo, &p.b_lo, &full_bar[stage], kb * BK, n_blk * BN);
-          if (++stage == p.num_stages) {
-            stage = 0;
-            phase ^= 1;
+        }
+        __syncwarp();
+        if (++as == p.a_stages) {
+          as = 0;
+          aphase ^= 1;
+        }
+        for (int bi = 0; bi < p.b_per_a; ++bi) {
+          mbar_wait(&b_empty[bs], bphase ^ 1);
+          if (lane == 0) VB_TRACE_EVENT(0, tr_p);
+          ++tr_p;
+          uint8_t* b_hi = b_ring + (size_t)bs * b_stage_bytes;
+          uint8_t* b_lo = b_hi + B_TILE;
+          // weight k-block: modes 0/1 -> ac; halo -> tap bi, channel block ac
+          const int kb = (p.a_mode == 2) ? (bi * p.a_chunks + ac) : ac;
+          if (elect_one()) {
+            mbar_expect_tx(&b_full[bs], b_stage_bytes);
+            tma_load_2d(b_hi, &p.b_hi, &b_full[bs], kb * BK, n_blk * BN);
+            if (planes == 2) tma_load_2d(b_lo, &p.b_lo, &b_full[bs], kb * BK, n_blk * BN);
+          }
+          __syncwarp();
+          if (++bs == p.b_stages) {
+            bs = 0;
+            bphase ^= 1;
           }
         }
       }
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(UMMA_FMT_BF16, BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int local_t = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_t) {
-        const int acc = local_t & 1;
-        const uint32_t acc_phase = (local_t >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+    constexpr uint32_t idesc = make_idesc(UMMA_FMT_BF16, BM, BN);
+    int as = 0, bs = 0;
+    uint32_t aphase = 0, bphase = 0;
+    int local_t = 0;
+    int tr_m = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_t) {
+      const int acc = local_t & 1;
+      const uint32_t acc_phase = (local_t >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      uint32_t accumulate = 0;
+      for (int ac = 0; ac < p.a_chunks; ++ac) {
+        mbar_wait(&a_full[as], aphase);
+        const uint32_t a_hi0 = smem_u32(a_ring + (size_t)as * a_stage_bytes);
+        for (int bi = 0; bi < p.b_per_a; ++bi) {
+          mbar_wait(&b_full[bs], bphase);
           tc_fence_after_sync();
-          const uint32_t st = smem_u32(stages + (size_t)stage * stage_bytes);
-          const uint32_t a_hi = st, a_lo = st + A_TILE;
-          const uint32_t b_hi = st + A_TILE * planes, b_lo = b_hi + B_TILE;
+          if (lane == 0) VB_TRACE_EVENT(1, tr_m);
+          // halo mode: filter tap (r, s) = rows shifted by r*(W+2)+s inside the halo tile
+          const uint32_t a_off = (p.a_mode == 2) ? (uint32_t)((bi / 3) * p.Wp + (bi % 3)) * 128u : 0u;
+          const uint32_t b_hi = smem_u32(b_ring + (size_t)bs * b_stage_bytes);
+          // descriptors of the first k-step; the next ones advance the 16-byte-unit start address by 2 (32 bytes)
+          const uint64_t da_hi0 = make_smem_desc(a_hi0 + a_off, 16, 1024, UMMA_LAYOUT_SW128);
+          const uint64_t da_lo0 = make_smem_desc(a_hi0 + a_off + p.a_plane_bytes, 16, 1024, UMMA_LAYOUT_SW128);
+          const uint64_t db_hi0 = make_smem_desc(b_hi, 16, 1024, UMMA_LAYOUT_SW128);
+          const uint64_t db_lo0 = make_smem_desc(b_hi + B_TILE, 16, 1024, UMMA_LAYOUT_SW128);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint32_t koff = k * UMMA_K * 2;   // bytes inside the 128-byte swizzle row
-            const uint64_t da_hi = make_smem_desc(a_hi + koff, 16, 1024, UMMA_LAYOUT_SW128);
-            const uint64_t db_hi = make_smem_desc(b_hi + koff, 16, 1024, UMMA_LAYOUT_SW128);
-            if (planes == 2) {
-              const uint64_t da_lo = make_smem_desc(a_lo + koff, 16, 1024, UMMA_LAYOUT_SW128);
-              const uint64_t db_lo = make_smem_desc(b_lo + koff, 16, 1024, UMMA_LAYOUT_SW128);
-              // small cross terms first, dominant term last
-              umma_bf16(d_tmem, da_lo, db_hi, idesc, (kb | k) != 0);
-              umma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
-              umma_bf16(d_tmem, da_hi, db_hi, idesc, 1);
-            } else {
-              umma_bf16(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t kadv = (uint64_t)(k * UMMA_K * 2 / 16);
+              if (planes == 2) {
+                // small cross terms first, dominant term last
+                umma_bf16(d_tmem, da_lo0 + kadv, db_hi0 + kadv, idesc, accumulate);
+                umma_bf16(d_tmem, da_hi0 + kadv, db_lo0 + kadv, idesc, 1);
+                umma_bf16(d_tmem, da_hi0 + kadv, db_hi0 + kadv, idesc, 1);
+              } else {
+                umma_bf16(d_tmem, da_hi0 + kadv, db_hi0 + kadv, idesc, accumulate);
+              }
+              accumulate = 1;
             }
+            umma_commit(&b_empty[bs]);             // frees the weight slot when these MMAs retire
+            if (bi == p.b_per_a - 1) umma_commit(&a_empty[as]);   // ... and the activation slot after its last tap
+            if (bi == p.b_per_a - 1 && ac == p.a_chunks - 1) umma_commit(&tmem_full[acc]);   // accumulator ready
           }
-          umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
-          if (++stage == p.num_stages) {
-            stage = 0;
-            phase ^= 1;
+          __syncwarp();
+          accumulate = 1;
+          if (lane == 0) VB_TRACE_EVENT(2, tr_m);
+          ++tr_m;
+          if (++bs == p.b_stages) {
+            bs = 0;
+            bphase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);              // accumulator ready for the epilogue
+        if (++as == p.a_stages) {
+          as = 0;
+          aphase ^= 1;
+        }
       }
     }
-    __syncwarp();
   } else {
     // ======================= epilogue (warps 2..5) =======================
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const int etid = threadIdx.x - 64;             // 0..127
     const bool store_leader = (etid == 0);
+    // halo mode: which output pixel (if any) this accumulator row is
+    int hy = 0, hx = 0;
+    if (p.a_mode == 2) {
+      hy = row / p.Wp;
+      hx = row - hy * p.Wp;
+    }
     int local_t = 0;
     int cur_n_blk = -1;
     bool store_pending = false;
@@ -199,16 +310,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       const int n_blk = tile / p.num_m_blocks;
       const int acc = local_t & 1;
       const uint32_t acc_phase = (local_t >> 1) & 1;
+      int img = 0, y0 = 0;
+      bool valid = true;
+      int srow = row;                              // row inside the staging tile
+      if (p.a_mode == 2) {
+        img = m_blk / p.tiles_per_img;
+        y0 = (m_blk - img * p.tiles_per_img) * p.TH;
+        valid = (hy < p.TH) && (hx < p.W) && (y0 + hy < p.H);
+        srow = hy * p.W + hx;
+      }
       if (p.stats != nullptr && n_blk != cur_n_blk) {
         if (cur_n_blk >= 0) {
           named_bar_sync(1, 128);
           for (int i = etid; i < BN; i += 128) {
-            if (cur_n_blk * BN + i < p.N) {
-              atomicAdd(&p.stats[cur_n_blk * BN + i], smem_stats[i]);
-              atomicAdd(&p.stats[p.N + cur_n_blk * BN + i], smem_stats[BN + i]);
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              a += smem_stats[w * 2 * BN + i];
+              b += smem_stats[w * 2 * BN + BN + i];
+              smem_stats[w * 2 * BN + i] = 0.0;
+              smem_stats[w * 2 * BN + BN + i] = 0.0;
             }
-            smem_stats[i] = 0.0;
-            smem_stats[BN + i] = 0.0;
+            if (cur_n_blk * BN + i < p.N) {
+              atomicAdd(&p.stats[cur_n_blk * BN + i], a);
+              atomicAdd(&p.stats[p.N + cur_n_blk * BN + i], b);
+            }
           }
           named_bar_sync(1, 128);
         }
@@ -216,6 +342,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
+      if (etid == 0) VB_TRACE_EVENT(3, local_t);
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 32; ++chunk) {
         uint32_t raw[32];
@@ -228,7 +355,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         }
         float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        for (int i = 0; i < 32; ++i) v[i] = valid ? __uint_as_float(raw[i]) : 0.f;
         const int c0 = n_blk * BN + chunk * 32;
         if (p.stats != nullptr) {
           // butterfly transpose-reduce: afterwards lane L holds the sum over the warp's 32 rows of channel c0+L
@@ -248,8 +375,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
               s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
             }
           }
-          atomicAdd(&smem_stats[chunk * 32 + lane], (double)s1[0]);
-          atomicAdd(&smem_stats[BN + chunk * 32 + lane], (double)s2[0]);
+          // warp-private fp64 accumulators: lane L owns channel chunk*32+L of this warp's slice, no atomics needed
+          double* my = smem_stats + quarter * 2 * BN + chunk * 32 + lane;
+          my[0] += (double)s1[0];
+          my[BN] += (double)s2[0];
         }
         if (p.scale != nullptr) {
 #pragma unroll
@@ -266,30 +395,65 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         // staging buffer must have been drained by the previous TMA store
         if (store_leader && store_pending) tma_store_wait_read0();
         named_bar_sync(2, 128);
-        {
-          // 128-byte row `row`, 16-byte chunk j stored at (j ^ (row & 7)) : SWIZZLE_128B, conflict-free
-          uint8_t* rowp = staging + row * 128;
+        if (valid) {
+          // 128-byte row `srow`, 16-byte chunk j stored at (j ^ (srow & 7)) : SWIZZLE_128B, conflict-free
+          uint8_t* rowp = staging + srow * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 f = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            *reinterpret_cast<float4*>(rowp + ((j ^ (row & 7)) << 4)) = f;
+            *reinterpret_cast<float4*>(rowp + ((j ^ (srow & 7)) << 4)) = f;
           }
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
         if (store_leader) {
-          tma_store_2d(&p.out, staging, c0, m_blk * BM);
+          if (p.a_mode == 2) tma_store_4d(&p.out, staging, c0, 0, y0, img);
+          else tma_store_2d(&p.out, staging, c0, m_blk * BM);
           tma_store_commit();
         }
         store_pending = true;
       }
     }
-    if (p.stats != nullptr && cur_n_blk >= 0) {
-      named_bar_sync(1, 128);
-      for (int i = etid; i < BN; i += 128) {
-        if (cur_n_blk * BN + i < p.N) {
-          atomicAdd(&p.stats[cur_n_blk * BN + i], smem_stats[i]);
-          atomicAdd(&p.stats[p.N + cur_n_blk * BN + i], smem_stats[BN + i]);
+    if (p.stats != nullptr) {
+      if (cur_n_blk >= 0) {
+        named_bar_sync(1, 128);
+        for (int i = etid; i < BN; i += 128) {
+          double a = 0.0, b = 0.0;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) a += smem_stats[w * 2 * BN + i], b += smem_stats[w * 2 * BN + BN + i];
+          if (cur_n_blk * BN + i < p.N) {
+            atomicAdd(&p.stats[cur_n_blk * BN + i], a);
+            atomicAdd(&p.stats[p.N + cur_n_blk * BN + i], b);
+          }
+        }
+      }
+      if (p.bn_coef != nullptr) {
+        // The last CTA to arrive owns the BatchNorm finalize: batch mean / biased variance -> per-channel
+        // scale = gamma / sqrt(var + eps), shift = beta - mean * scale, running stats with the unbiased variance.
+        __threadfence();
+        named_bar_sync(1, 128);
+        if (etid == 0) {
+          const unsigned int ticket = atomicAdd(p.bn_counter, 1u);
+          *last_flag = (ticket == gridDim.x - 1) ? 1u : 0u;
+        }
+        named_bar_sync(1, 128);
+        if (*last_flag) {
+          __threadfence();
+          for (int c = etid; c < p.N; c += 128) {
+            const double mean = __ldcg(&p.stats[c]) / p.bn_count;
+            double var = __ldcg(&p.stats[p.N + c]) / p.bn_count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const double unbiased = p.bn_count > 1.0 ? var * (p.bn_count / (p.bn_count - 1.0)) : var;
+            p.bn_running_mean[c] =
+                (float)((1.0 - (double)p.bn_momentum) * (double)p.bn_running_mean[c] + (double)p.bn_momentum * mean);
+            p.bn_running_var[c] =
+                (float)((1.0 - (double)p.bn_momentum) * (double)p.bn_running_var[c] + (double)p.bn_momentum * unbiased);
+            const float inv = (float)(1.0 / sqrt(var + (double)p.bn_eps));
+            const float sc = p.bn_gamma[c] * inv;
+            p.bn_coef[c] = sc;
+            p.bn_coef[p.N + c] = p.bn_beta[c] - (float)mean * sc;
+          }
+          if (etid == 0 && p.bn_nbt != nullptr) *p.bn_nbt += 1;
         }
       }
     }
@@ -302,6 +466,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 2 * BN);
   }
+}
+
+// eval-mode BatchNorm: per-channel scale/shift from the running statistics
+__global__ void bn_eval_coef_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                                    float* __restrict__ coef, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float inv = (float)(1.0 / sqrt((double)rv[c] + (double)eps));
+  const float sc = gamma[c] * inv;
+  coef[c] = sc;
+  coef[C + c] = beta[c] - rm[c] * sc;
+}
+
+int bn_eval_coef_launch(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, float* coef,
+                        int C, cudaStream_t stream) {
+  if (C == 0) return VB_OK;
+  bn_eval_coef_kernel<<<(C + 127) / 128, 128, 0, stream>>>(gamma, beta, rm, rv, eps, coef, C);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -318,23 +502,63 @@ static int num_sms() {
   return g_num_sms;
 }
 
-static size_t gemm_smem_bytes(int bn, int passes, int* stages_out) {
-  const size_t planes = passes == 3 ? 2 : 1;
-  const size_t stage = (size_t)(BM * 128 + bn * 128) * planes;
-  const size_t fixed = 1024 /*align slack*/ + STAGING_BYTES + (2 * MAX_STAGES + 4) * 8 + 16 + 2 * bn * 8;
-  const size_t budget = 227 * 1024;
-  int stages = (int)((budget - fixed) / stage);
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  *stages_out = stages;
-  return fixed + stage * stages;
+constexpr size_t SMEM_BUDGET = 227 * 1024;
+static size_t fixed_smem(int bn) {
+  return 1024 /*align slack*/ + STAGING_BYTES + (4 * MAX_RING + 4) * 8 + 16 + 8 * bn * 8;
 }
 
 template <int BN>
-static int launch_gemm(const GemmKernelParams& kp, int stages, size_t smem, int grid, cudaStream_t stream) {
+static int launch_gemm(const GemmKernelParams& kp, size_t smem, int grid, cudaStream_t stream) {
   VB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   conv_gemm_kernel<BN><<<grid, GEMM_THREADS, smem, stream>>>(kp);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
+}
+
+// Tile width policy.  Measured on B200 (profiles/r01_conv_timeline.md): a tcgen05.mma dispatch from shared-memory
+// operands costs ~22 cycles + max(48, N/2) cycles and every k-block adds ~270 cycles of barrier / descriptor work in
+// the single issuing thread, so wider tiles amortise better - unless they leave SMs idle in the last wave.
+static int auto_block_n(const ConvGemmDesc& d) {
+  const int cands[3] = {256, 128, 64};
+  const long m_blocks = (d.M + BM - 1) / BM;
+  const long sms = num_sms();
+  long best_cost = -1;
+  int best = 64;
+  for (int bn : cands) {
+    if (d.N % bn != 0 && !(bn == 64 && d.N < 128)) continue;
+    if (bn == 64 && d.N % 64 != 0 && d.N > 64) continue;
+    const long tiles = m_blocks * ((d.N + bn - 1) / bn);
+    const long waves = (tiles + sms - 1) / sms;
+    const long dispatch = 22 + (bn / 2 > 48 ? bn / 2 : 48);
+    const long passes = d.passes == 3 ? 3 : 1;
+    const long mainloop = (long)(d.K / BK) * (4 * passes * dispatch + 270);
+    const long epilogue = 900L * (bn / 32);          // overlaps the next tile's main loop (double-buffered TMEM)
+    const long cost = waves * (mainloop > epilogue ? mainloop : epilogue);
+    if (best_cost < 0 || cost < best_cost) best_cost = cost, best = bn;
+  }
+  return best;
+}
+
+// Can this convolution run in HALO mode, and with which tile height?
+static int halo_tile_rows(const ConvGemmDesc& d) {
+  if (!d.im2col || d.halo_mode == 0) return 0;
+  if (!(d.R == 3 && d.S == 3 && d.stride == 1 && d.pad_lo_h == 1 && d.pad_lo_w == 1 && d.pad_hi_h == 1 && d.pad_hi_w == 1))
+    return 0;
+  const int Wp = d.W + 2;
+  if (Wp > BM) return 0;
+  int th = BM / Wp;
+  if (th > d.H) th = d.H;
+  const int tiles_per_img = (d.H + th - 1) / th;
+  // useful fraction of the MMA rows; below ~70% the plain im2col path wins
+  const double eff = (double)(d.H * d.W) / ((double)tiles_per_img * BM);
+  if (d.halo_mode < 0 && eff < 0.7) return 0;
+  // two halo stages + at least two weight stages must fit in shared memory, else fall back to im2col
+  int bn = d.block_n ? d.block_n : auto_block_n(d);
+  const size_t planes = d.passes == 3 ? 2 : 1;
+  const size_t a_stage = (size_t)(((th + 2) * Wp + 7) / 8) * 1024 * planes;
+  const size_t b_stage = (size_t)bn * 128 * planes;
+  if (fixed_smem(bn) + 2 * a_stage + 2 * b_stage > SMEM_BUDGET) return 0;
+  return th;
 }
 
 int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
@@ -345,9 +569,12 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   VB_REQUIRE(d.a_hi && d.b_hi && d.out, "conv_gemm: null operand");
   VB_REQUIRE(d.passes == 1 || (d.a_lo && d.b_lo), "conv_gemm: bf16x3 needs lo planes");
   VB_REQUIRE(!(d.stats && (d.bias || d.scale || d.relu)), "conv_gemm: stats are defined on raw accumulators only");
+  VB_REQUIRE(!d.bn_coef || (d.stats && d.bn_gamma && d.bn_beta && d.bn_running_mean && d.bn_running_var && d.bn_counter),
+             "conv_gemm: BatchNorm finalize needs stats, gamma, beta, running stats and a counter");
   int bn = d.block_n;
-  if (bn == 0) bn = (d.N % 128 == 0) ? 128 : 64;
+  if (bn == 0) bn = auto_block_n(d);
   VB_REQUIRE(bn == 64 || bn == 128 || bn == 256, "conv_gemm: block_n must be 64/128/256");
+  const size_t planes = d.passes == 3 ? 2 : 1;
 
   GemmKernelParams kp;
   memset(&kp, 0, sizeof(kp));
@@ -355,19 +582,56 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   kp.N = d.N;
   kp.num_m_blocks = (d.M + BM - 1) / BM;
   kp.num_n_blocks = (d.N + bn - 1) / bn;
-  kp.num_k_blocks = d.K / BK;
   kp.passes = d.passes;
   kp.scale = d.scale;
   kp.bias = d.bias;
   kp.relu = d.relu;
   kp.stats = d.stats;
+  kp.bn_gamma = d.bn_gamma, kp.bn_beta = d.bn_beta, kp.bn_running_mean = d.bn_running_mean;
+  kp.bn_running_var = d.bn_running_var, kp.bn_nbt = reinterpret_cast<long long*>(d.bn_num_batches_tracked);
+  kp.bn_coef = d.bn_coef, kp.bn_counter = d.bn_counter, kp.bn_momentum = d.bn_momentum, kp.bn_eps = d.bn_eps;
+  kp.bn_count = (double)d.M;
+  kp.trace = reinterpret_cast<unsigned long long*>(d.trace);
+  kp.a_plane_bytes = BM * 128;
+  kp.a_tx_bytes = BM * 128;
+  kp.a_chunks = d.K / BK;
+  kp.b_per_a = 1;
   int rc;
+  const int th = halo_tile_rows(d);
   if (d.im2col) {
     VB_REQUIRE(d.Cin % BK == 0, "conv_gemm: Cin=%d must be a multiple of %d", d.Cin, BK);
     VB_REQUIRE(d.K == d.R * d.S * d.Cin, "conv_gemm: K != R*S*Cin");
     const int P = (d.H + d.pad_lo_h + d.pad_hi_h - d.R) / d.stride + 1;
     const int Q = (d.W + d.pad_lo_w + d.pad_hi_w - d.S) / d.stride + 1;
     VB_REQUIRE(d.M == d.batch * P * Q, "conv_gemm: M=%d != batch*P*Q=%d", d.M, d.batch * P * Q);
+    kp.cin_blocks = d.Cin / BK;
+  }
+  if (th > 0) {
+    // ---- HALO mode ----
+    const int Wp = d.W + 2;
+    kp.a_mode = 2;
+    kp.Wp = Wp, kp.TH = th, kp.H = d.H, kp.W = d.W;
+    kp.tiles_per_img = (d.H + th - 1) / th;
+    kp.num_m_blocks = d.batch * kp.tiles_per_img;
+    kp.a_chunks = kp.cin_blocks;
+    kp.b_per_a = 9;
+    const uint32_t halo_rows = (uint32_t)(th + 2) * Wp;
+    kp.a_tx_bytes = halo_rows * 128;
+    kp.a_plane_bytes = ((halo_rows + 7) / 8) * 1024;
+    rc = encode_tma_4d_nhwc(&kp.a_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d.a_hi, d.batch, d.H, d.W, d.Cin, BK, Wp, th + 2,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    if (d.passes == 3) {
+      rc = encode_tma_4d_nhwc(&kp.a_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d.a_lo, d.batch, d.H, d.W, d.Cin, BK, Wp,
+                              th + 2, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+    rc = encode_tma_4d_nhwc(&kp.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.out, d.batch, d.H, d.W, d.N, 32, d.W, th,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  } else if (d.im2col) {
+    const int P = (d.H + d.pad_lo_h + d.pad_hi_h - d.R) / d.stride + 1;
+    const int Q = (d.W + d.pad_lo_w + d.pad_hi_w - d.S) / d.stride + 1;
     kp.a_mode = 1;
     kp.PQ = P * Q;
     kp.Q = Q;
@@ -375,7 +639,6 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
     kp.pad_h = d.pad_lo_h;
     kp.pad_w = d.pad_lo_w;
     kp.S = d.S;
-    kp.cin_blocks = d.Cin / BK;
     rc = encode_tma_im2col_nhwc(&kp.a_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d.a_hi, d.batch, d.H, d.W, d.Cin, d.pad_lo_h,
                                 d.pad_lo_w, d.pad_hi_h, d.pad_hi_w, d.R, d.S, d.stride, BK, BM,
                                 CU_TENSOR_MAP_SWIZZLE_128B);
@@ -405,19 +668,33 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
                        CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  rc = encode_tma_2d(&kp.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.out, d.N, d.M, (uint64_t)d.N * 4, 32, BM,
-                     CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc) return rc;
+  if (kp.a_mode != 2) {
+    rc = encode_tma_2d(&kp.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.out, d.N, d.M, (uint64_t)d.N * 4, 32, BM,
+                       CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
 
-  int stages = 0;
-  const size_t smem = gemm_smem_bytes(bn, d.passes, &stages);
-  VB_REQUIRE(stages >= 2, "conv_gemm: not enough shared memory for a 2-stage pipeline (bn=%d)", bn);
-  kp.num_stages = stages;
+  // ---- shared-memory budget: A ring + B ring ----
+  const size_t a_stage = (size_t)kp.a_plane_bytes * planes;
+  const size_t b_stage = (size_t)bn * 128 * planes;
+  const size_t avail = SMEM_BUDGET - fixed_smem(bn);
+  if (kp.a_mode == 2) {
+    kp.a_stages = 2;
+    VB_REQUIRE(avail > 2 * a_stage + 2 * b_stage, "conv_gemm: halo tile does not fit in shared memory");
+    int bs = (int)((avail - 2 * a_stage) / b_stage);
+    kp.b_stages = bs > MAX_RING ? MAX_RING : bs;
+  } else {
+    int st = (int)(avail / (a_stage + b_stage));
+    if (st > MAX_RING) st = MAX_RING;
+    VB_REQUIRE(st >= 2, "conv_gemm: not enough shared memory for a 2-stage pipeline (bn=%d)", bn);
+    kp.a_stages = kp.b_stages = st;
+  }
+  const size_t smem = fixed_smem(bn) + kp.a_stages * a_stage + kp.b_stages * b_stage;
   const int tiles = kp.num_m_blocks * kp.num_n_blocks;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  if (bn == 64) return launch_gemm<64>(kp, stages, smem, grid, stream);
-  if (bn == 128) return launch_gemm<128>(kp, stages, smem, grid, stream);
-  return launch_gemm<256>(kp, stages, smem, grid, stream);
+  if (bn == 64) return launch_gemm<64>(kp, smem, grid, stream);
+  if (bn == 128) return launch_gemm<128>(kp, smem, grid, stream);
+  return launch_gemm<256>(kp, smem, grid, stream);
 }
 
 }  // namespace vb

@@ -29,50 +29,62 @@ __device__ __forceinline__ float4 join4(const bf16x4& hi, const bf16x4& lo) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// stem packing
+// stem packing: one block per (image n, row pair j).  The six input rows (2 image rows x 3 channels) are staged
+// in shared memory with coalesced loads (every input row belongs to exactly one j, so the image is read once),
+// then each thread emits 16-byte groups of the 64-element packed "pixel" for consecutive q.
 // ------------------------------------------------------------------------------------------------
-__global__ void stem_pack_kernel(const float* __restrict__ x, const int64_t* __restrict__ gather_idx,
-                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int N, int H, int W,
-                                 int Hj, int Q, int64_t total_groups) {
-  // one thread per 8-element group of one (n, j, q) "pixel": consecutive threads write consecutive 16-byte groups
-  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_groups;
-       g += (int64_t)gridDim.x * blockDim.x) {
-    const int grp = (int)(g & 7);
-    int64_t pix = g >> 3;
-    const int q = (int)(pix % Q);
-    pix /= Q;
-    const int j = (int)(pix % Hj);
-    const int n = (int)(pix / Hj);
-    const int64_t src_n = gather_idx ? gather_idx[n] : n;
-    const float* xn = x + src_n * 3 * (int64_t)H * W;
+__global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ x,
+                                                        const int64_t* __restrict__ gather_idx,
+                                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                        int H, int W, int Hj, int Q) {
+  extern __shared__ float rows[];                 // [6][W + 6], 3 zero columns of left padding
+  __shared__ int lut[64];                         // element e -> offset of (r2, c, s) inside `rows`, or -1
+  const int j = blockIdx.x;
+  const int n = blockIdx.y;
+  const int Wp = W + 6;
+  const int tid = threadIdx.x;
+  if (tid < 64) {
+    int off = -1;
+    if (tid < 42) {
+      const int r2 = tid / 21, rem = tid - r2 * 21, s = rem / 3, c = rem - s * 3;
+      off = (r2 * 3 + c) * Wp + s;
+    }
+    lut[tid] = off;
+  }
+  const int64_t src_n = gather_idx ? gather_idx[n] : n;
+  const float* xn = x + src_n * 3 * (int64_t)H * W;
+  for (int i = tid; i < 6 * Wp; i += blockDim.x) {
+    const int rc = i / Wp, col = i - rc * Wp - 3;
+    const int r2 = rc / 3, c = rc - r2 * 3;
+    const int row = 2 * j - 1 + r2;
+    float v = 0.f;
+    if (row >= 0 && row < H && col >= 0 && col < W) v = __ldg(xn + ((int64_t)c * H + row) * W + col);
+    rows[i] = v;
+  }
+  __syncthreads();
+  const int64_t base = (((int64_t)n * Hj + j) * Q) * 64;
+  for (int g = tid; g < Q * 8; g += blockDim.x) {
+    const int q = g >> 3, grp = g & 7;
     bf16x8 oh, ol;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int e = grp * 8 + i;
-      float val = 0.f;
-      if (e < 42) {
-        const int r2 = e / 21;
-        const int rem = e - r2 * 21;
-        const int s = rem / 3;
-        const int c = rem - s * 3;
-        const int row = 2 * j - 1 + r2;
-        const int col = 2 * q - 3 + s;
-        if (row >= 0 && row < H && col >= 0 && col < W) val = __ldg(xn + ((int64_t)c * H + row) * W + col);
-      }
+      const int off = lut[grp * 8 + i];
+      const float val = off >= 0 ? rows[off + 2 * q] : 0.f;
       split_bf16(val, oh.v[i], ol.v[i]);
     }
-    *reinterpret_cast<bf16x8*>(hi + g * 8) = oh;
-    if (lo) *reinterpret_cast<bf16x8*>(lo + g * 8) = ol;
+    *reinterpret_cast<bf16x8*>(hi + base + (int64_t)g * 8) = oh;
+    if (lo) *reinterpret_cast<bf16x8*>(lo + base + (int64_t)g * 8) = ol;
   }
 }
 
 int stem_pack_launch(const float* x, const int64_t* gather_idx, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int H,
                      int W, int Hj, int Q, cudaStream_t stream) {
-  const int64_t groups = (int64_t)N * Hj * Q * 8;
-  if (groups == 0) return VB_OK;
-  const int threads = 256;
-  const int blocks = (int)((groups + threads - 1) / threads > 148 * 64 ? 148 * 64 : (groups + threads - 1) / threads);
-  stem_pack_kernel<<<blocks, threads, 0, stream>>>(x, gather_idx, hi, lo, N, H, W, Hj, Q, groups);
+  if (N == 0) return VB_OK;
+  VB_REQUIRE(N <= 65535, "stem_pack: batch %d too large", N);
+  const size_t smem = (size_t)6 * (W + 6) * sizeof(float);
+  VB_REQUIRE(smem <= 48 * 1024, "stem_pack: image width %d too large", W);
+  dim3 grid(Hj, N);
+  stem_pack_kernel<<<grid, 256, smem, stream>>>(x, gather_idx, hi, lo, H, W, Hj, Q);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }
@@ -126,50 +138,21 @@ int weight_prep_launch(const WeightPrepEntry* table_dev, int n_entries, int64_t 
 }
 
 // ------------------------------------------------------------------------------------------------
-// BatchNorm scale/shift for 4 consecutive channels, from batch sums (train) or running stats (eval)
+// BatchNorm is applied from per-channel (scale, shift) pairs `coef[2][C]` produced by the convolution kernel's fused
+// finalize (train mode) or by bn_eval_coef (eval mode): these kernels are pure fp32 streaming passes.
 // ------------------------------------------------------------------------------------------------
 struct BnSideDev {
   const float* raw;
-  const double* stats;
-  const float* gamma;
-  const float* beta;
-  float* running_mean;
-  float* running_var;
-  int64_t* nbt;
+  const float* coef;
 };
 static BnSideDev to_dev(const BnSide& s) {
   BnSideDev d;
-  d.raw = s.raw, d.stats = s.stats, d.gamma = s.gamma, d.beta = s.beta;
-  d.running_mean = s.running_mean, d.running_var = s.running_var, d.nbt = s.num_batches_tracked;
+  d.raw = s.raw, d.coef = s.coef;
   return d;
 }
-
-__device__ __forceinline__ void bn_coeffs4(const BnSideDev& s, int c, int C, double count, float eps, float momentum,
-                                           bool update_running, float4& sc, float4& sh) {
-  float scv[4], shv[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    double mean, var;
-    if (s.stats) {
-      mean = s.stats[c + i] / count;
-      var = s.stats[C + c + i] / count - mean * mean;
-      if (var < 0.0) var = 0.0;
-      if (update_running) {
-        const double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
-        s.running_mean[c + i] = (float)((1.0 - momentum) * (double)s.running_mean[c + i] + momentum * mean);
-        s.running_var[c + i] = (float)((1.0 - momentum) * (double)s.running_var[c + i] + momentum * unbiased);
-      }
-    } else {
-      mean = (double)s.running_mean[c + i];
-      var = (double)s.running_var[c + i];
-    }
-    // the reference's BatchNorm evaluates in fp32: x * (gamma * rsqrt(var + eps)) + (beta - mean * scale)
-    const float inv = (float)(1.0 / sqrt(var + (double)eps));
-    scv[i] = s.gamma[c + i] * inv;
-    shv[i] = s.beta[c + i] - (float)mean * scv[i];
-  }
-  sc = make_float4(scv[0], scv[1], scv[2], scv[3]);
-  sh = make_float4(shv[0], shv[1], shv[2], shv[3]);
+__device__ __forceinline__ void bn_coeffs4(const BnSideDev& s, int c, int C, float4& sc, float4& sh) {
+  sc = __ldg(reinterpret_cast<const float4*>(s.coef + c));
+  sh = __ldg(reinterpret_cast<const float4*>(s.coef + C + c));
 }
 
 __device__ __forceinline__ float4 fma4(const float4& x, const float4& a, const float4& b) {
@@ -192,7 +175,7 @@ __device__ __forceinline__ float4 max4(const float4& a, const float4& b) {
 __global__ void bn_apply_kernel(BnSideDev main, int res_kind, const __nv_bfloat16* __restrict__ res_hi,
                                 const __nv_bfloat16* __restrict__ res_lo, BnSideDev res_bn, int relu,
                                 __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
-                                float* __restrict__ out_f32, int64_t M, int C, float momentum, float eps) {
+                                float* __restrict__ out_f32, int64_t M, int C) {
   const int C4 = C >> 2;
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t gthreads = (int64_t)gridDim.x * blockDim.x;
@@ -200,14 +183,9 @@ __global__ void bn_apply_kernel(BnSideDev main, int res_kind, const __nv_bfloat1
   const int64_t row0 = gtid / C4;
   const int64_t row_stride = gthreads / C4;
   const int c = cg * 4;
-  const bool updater = (row0 == 0);       // exactly one thread per channel group updates the running stats
   float4 sc, sh, rsc, rsh;
-  bn_coeffs4(main, c, C, (double)M, eps, momentum, updater, sc, sh);
-  if (res_kind == 2) bn_coeffs4(res_bn, c, C, (double)M, eps, momentum, updater, rsc, rsh);
-  if (gtid == 0) {
-    if (main.stats && main.nbt) *main.nbt += 1;
-    if (res_kind == 2 && res_bn.stats && res_bn.nbt) *res_bn.nbt += 1;
-  }
+  bn_coeffs4(main, c, C, sc, sh);
+  if (res_kind == 2) bn_coeffs4(res_bn, c, C, rsc, rsh);
   for (int64_t r = row0; r < M; r += row_stride) {
     const int64_t off = r * C + c;
     float4 v = fma4(__ldcs(reinterpret_cast<const float4*>(main.raw + off)), sc, sh);
@@ -246,7 +224,7 @@ static int elementwise_grid(int64_t work_threads, int C4, int threads) {
 
 int bn_apply_launch(const BnSide& main, int res_kind, const __nv_bfloat16* res_hi, const __nv_bfloat16* res_lo,
                     const BnSide& res_bn, int relu, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, float* out_f32,
-                    int64_t M, int C, float momentum, float eps, cudaStream_t stream) {
+                    int64_t M, int C, cudaStream_t stream) {
   VB_REQUIRE(C % 4 == 0, "bn_apply: C=%d must be a multiple of 4", C);
   const int C4 = C / 4;
   const int threads = 256;
@@ -255,60 +233,68 @@ int bn_apply_launch(const BnSide& main, int res_kind, const __nv_bfloat16* res_h
   if (M == 0) return VB_OK;
   const int blocks = elementwise_grid(M * C4, C4, threads);
   bn_apply_kernel<<<blocks, threads, 0, stream>>>(to_dev(main), res_kind, res_hi, res_lo, to_dev(res_bn), relu, out_hi,
-                                                  out_lo, out_f32, M, C, momentum, eps);
+                                                  out_lo, out_f32, M, C);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-// stem: bn + relu + maxpool 3x3 stride 2 pad 1 (NHWC); padding behaves as -inf (torch max_pool2d)
+// stem: bn + relu + maxpool 3x3 stride 2 pad 1 (NHWC); padding behaves as -inf (torch max_pool2d).
+// One block per (image, output row, tile of MP_TQ output columns): the 3 x (2*MP_TQ+1) input pixels are normalised
+// once while being staged in shared memory (coalesced 16-byte loads), then reduced.
 // ------------------------------------------------------------------------------------------------
-__global__ void bn_relu_maxpool_kernel(BnSideDev bn, __nv_bfloat16* __restrict__ out_hi,
-                                       __nv_bfloat16* __restrict__ out_lo, int N, int P, int Q, int C, int P2, int Q2,
-                                       float momentum, float eps) {
+constexpr int MP_TQ = 14;
+__global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(BnSideDev bn, __nv_bfloat16* __restrict__ out_hi,
+                                                              __nv_bfloat16* __restrict__ out_lo, int N, int P, int Q,
+                                                              int C, int P2, int Q2) {
+  extern __shared__ float4 tile4[];                   // [3][2*MP_TQ+1][C/4]
   const int C4 = C >> 2;
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t gthreads = (int64_t)gridDim.x * blockDim.x;
-  const int cg = (int)(gtid % C4);
-  const int c = cg * 4;
-  const int64_t pix0 = gtid / C4;
-  const int64_t pix_stride = gthreads / C4;
+  const int q2_0 = blockIdx.x * MP_TQ;
+  const int p2 = blockIdx.y;
+  const int n = blockIdx.z;
+  const int tid = threadIdx.x;
+  const int cols = 2 * MP_TQ + 1;
+  const int cg = tid % C4;
   float4 sc, sh;
-  bn_coeffs4(bn, c, C, (double)N * P * Q, eps, momentum, pix0 == 0, sc, sh);
-  if (gtid == 0 && bn.stats && bn.nbt) *bn.nbt += 1;
-  const int64_t total = (int64_t)N * P2 * Q2;
-  for (int64_t op = pix0; op < total; op += pix_stride) {
-    const int q2 = (int)(op % Q2);
-    const int64_t t = op / Q2;
-    const int p2 = (int)(t % P2);
-    const int n = (int)(t / P2);
-    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  bn_coeffs4(bn, cg * 4, C, sc, sh);
+  const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  // blockDim (256) is a multiple of C4, so a thread always serves the same channel group
+  for (int i = tid; i < 3 * cols * C4; i += blockDim.x) {
+    const int pix = i / C4;
+    const int dy = pix / cols, dx = pix - dy * cols;
+    const int y = 2 * p2 - 1 + dy, xx = 2 * q2_0 - 1 + dx;
+    float4 v = ninf;
+    if (y >= 0 && y < P && xx >= 0 && xx < Q)
+      v = relu4(fma4(__ldcs(reinterpret_cast<const float4*>(bn.raw + (((int64_t)n * P + y) * Q + xx) * C) + cg), sc, sh));
+    tile4[i] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < MP_TQ * C4; i += blockDim.x) {
+    const int t = i / C4;
+    const int q2 = q2_0 + t;
+    if (q2 >= Q2) break;
+    float4 m = ninf;
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const int y = 2 * p2 - 1 + dy;
-      if (y < 0 || y >= P) continue;
+    for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int xx = 2 * q2 - 1 + dx;
-        if (xx < 0 || xx >= Q) continue;
-        const float4 v = *reinterpret_cast<const float4*>(bn.raw + (((int64_t)n * P + y) * Q + xx) * C + c);
-        m = max4(m, relu4(fma4(v, sc, sh)));
-      }
-    }
+      for (int dx = 0; dx < 3; ++dx) m = max4(m, tile4[(dy * cols + 2 * t + dx) * C4 + cg]);
     bf16x4 h, l;
     split4(m, h, l);
-    *reinterpret_cast<bf16x4*>(out_hi + op * C + c) = h;
-    if (out_lo) *reinterpret_cast<bf16x4*>(out_lo + op * C + c) = l;
+    const int64_t off = ((((int64_t)n * P2 + p2) * Q2) + q2) * C + cg * 4;
+    *reinterpret_cast<bf16x4*>(out_hi + off) = h;
+    if (out_lo) *reinterpret_cast<bf16x4*>(out_lo + off) = l;
   }
 }
 
 int bn_relu_maxpool_launch(const BnSide& bn, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int N, int P, int Q, int C,
-                           int P2, int Q2, float momentum, float eps, cudaStream_t stream) {
-  VB_REQUIRE(C % 4 == 0 && 256 % (C / 4) == 0, "bn_relu_maxpool: unsupported channel count %d", C);
-  const int64_t work = (int64_t)N * P2 * Q2 * (C / 4);
-  if (work == 0) return VB_OK;
-  const int blocks = elementwise_grid(work, C / 4, 256);
-  bn_relu_maxpool_kernel<<<blocks, 256, 0, stream>>>(to_dev(bn), out_hi, out_lo, N, P, Q, C, P2, Q2, momentum, eps);
+                           int P2, int Q2, cudaStream_t stream) {
+  VB_REQUIRE(C % 4 == 0 && C <= 256 && 256 % (C / 4) == 0, "bn_relu_maxpool: unsupported channel count %d", C);
+  VB_REQUIRE(N <= 65535 && P2 <= 65535, "bn_relu_maxpool: shape too large");
+  if ((int64_t)N * P2 * Q2 == 0) return VB_OK;
+  const size_t smem = (size_t)3 * (2 * MP_TQ + 1) * (C / 4) * sizeof(float4);
+  VB_REQUIRE(smem <= 48 * 1024, "bn_relu_maxpool: channel count %d too large", C);
+  dim3 grid((Q2 + MP_TQ - 1) / MP_TQ, P2, N);
+  bn_relu_maxpool_kernel<<<grid, 256, smem, stream>>>(to_dev(bn), out_hi, out_lo, N, P, Q, C, P2, Q2);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }
@@ -321,21 +307,16 @@ constexpr int FP_CH = 32;
 __global__ void bn_final_pool_kernel(BnSideDev main, int res_kind, const __nv_bfloat16* __restrict__ res_hi,
                                      const __nv_bfloat16* __restrict__ res_lo, BnSideDev res_bn,
                                      const int64_t* __restrict__ scatter_idx, float* __restrict__ spatial,
-                                     float* __restrict__ pooled, int N, int HW, int C, float momentum, float eps) {
+                                     float* __restrict__ pooled, int N, int HW, int C) {
   extern __shared__ float tile[];                 // [FP_CH][HW + 1]
   const int n = blockIdx.y;
   const int c_base = blockIdx.x * FP_CH;
   const int tid = threadIdx.x;
   const int cg = tid & 7;                         // 8 channel groups of 4
   const int c = c_base + cg * 4;
-  const bool updater = (n == 0 && tid < 8);
   float4 sc, sh, rsc, rsh;
-  bn_coeffs4(main, c, C, (double)N * HW, eps, momentum, updater, sc, sh);
-  if (res_kind == 2) bn_coeffs4(res_bn, c, C, (double)N * HW, eps, momentum, updater, rsc, rsh);
-  if (n == 0 && blockIdx.x == 0 && tid == 0) {
-    if (main.stats && main.nbt) *main.nbt += 1;
-    if (res_kind == 2 && res_bn.stats && res_bn.nbt) *res_bn.nbt += 1;
-  }
+  bn_coeffs4(main, c, C, sc, sh);
+  if (res_kind == 2) bn_coeffs4(res_bn, c, C, rsc, rsh);
   const int ld = HW + 1;
   for (int pix = tid >> 3; pix < HW; pix += blockDim.x >> 3) {
     const int64_t off = ((int64_t)n * HW + pix) * C + c;
@@ -374,7 +355,7 @@ __global__ void bn_final_pool_kernel(BnSideDev main, int res_kind, const __nv_bf
 
 int bn_final_pool_launch(const BnSide& main, int res_kind, const __nv_bfloat16* res_hi, const __nv_bfloat16* res_lo,
                          const BnSide& res_bn, const int64_t* scatter_idx, float* spatial_nchw, float* pooled, int N,
-                         int HW, int C, float momentum, float eps, cudaStream_t stream) {
+                         int HW, int C, cudaStream_t stream) {
   VB_REQUIRE(C % FP_CH == 0, "bn_final_pool: C=%d must be a multiple of %d", C, FP_CH);
   const size_t smem = (size_t)FP_CH * (HW + 1) * sizeof(float);
   VB_REQUIRE(smem <= 200 * 1024, "bn_final_pool: spatial size %d too large", HW);
@@ -383,7 +364,7 @@ int bn_final_pool_launch(const BnSide& main, int res_kind, const __nv_bfloat16* 
     VB_CHECK_CUDA(cudaFuncSetAttribute(bn_final_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(C / FP_CH, N);
   bn_final_pool_kernel<<<grid, 256, smem, stream>>>(to_dev(main), res_kind, res_hi, res_lo, to_dev(res_bn), scatter_idx,
-                                                    spatial_nchw, pooled, N, HW, C, momentum, eps);
+                                                    spatial_nchw, pooled, N, HW, C);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }

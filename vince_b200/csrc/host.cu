@@ -86,6 +86,28 @@ int encode_tma_2d(CUtensorMap* map, CUtensorMapDataType dtype, const void* base,
   return VB_OK;
 }
 
+int encode_tma_4d_nhwc(CUtensorMap* map, CUtensorMapDataType dtype, const void* base, int N, int H, int W, int C,
+                       uint32_t box_c, uint32_t box_w, uint32_t box_h, CUtensorMapSwizzle swz) {
+  int rc = resolve();
+  if (rc) return rc;
+  const size_t eb = dtype_bytes(dtype);
+  VB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA 4d: base pointer %p not 16-byte aligned", base);
+  VB_REQUIRE(((size_t)C * eb) % 16 == 0, "TMA 4d: C*elem must be a multiple of 16 bytes (C=%d)", C);
+  VB_REQUIRE(box_c * eb <= 128 && box_w <= 256 && box_h <= 256, "TMA 4d: box too large");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * eb, (cuuint64_t)W * C * eb, (cuuint64_t)H * W * C * eb};
+  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_tiled(map, dtype, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d) failed (%d): N=%d H=%d W=%d C=%d box=%ux%ux%u", (int)r, N, H, W, C, box_c,
+              box_w, box_h);
+    return VB_ERR_CUDA;
+  }
+  return VB_OK;
+}
+
 // NHWC activation tensor viewed by TMA im2col mode.  The "bounding box" corners follow the cuDNN/CUTLASS
 // convention: lower = -pad_lo, upper = pad_hi - (filter - 1); base-pixel coordinates passed to the load are
 // (q*stride - pad_lo_w, p*stride - pad_lo_h, n) and the filter tap is passed as the {s, r} offsets.

@@ -90,20 +90,27 @@ __global__ void __launch_bounds__(NCE_THREADS, 1) infonce_main_kernel(const __gr
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // producer / MMA warps: warp-uniform control flow, one elected lane issues (keeps operands in uniform registers)
   if (warp == 0) {
-    if (lane == 0 && t_end > t_begin) {
-      mbar_expect_tx(q_full, q_bytes);
-      for (int a = 0; a < atoms; ++a) tma_load_2d(q_smem + a * NCE_BM * 128, &p.q_map, q_full, a * 32, m_blk * NCE_BM);
+    if (t_end > t_begin) {
+      if (elect_one()) {
+        mbar_expect_tx(q_full, q_bytes);
+        for (int a = 0; a < atoms; ++a) tma_load_2d(q_smem + a * NCE_BM * 128, &p.q_map, q_full, a * 32, m_blk * NCE_BM);
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = stages + (size_t)stage * stage_bytes;
-        mbar_expect_tx(&full_bar[stage], stage_bytes);
         const bool is_key = t < p.nkt;
         const CUtensorMap* map = is_key ? &p.keys_map : &p.queue_map;
         const int row0 = (is_key ? t : t - p.nkt) * NCE_BN;
-        for (int a = 0; a < atoms; ++a) tma_load_2d(st + a * NCE_BN * 128, map, &full_bar[stage], a * 32, row0);
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          for (int a = 0; a < atoms; ++a) tma_load_2d(st + a * NCE_BN * 128, map, &full_bar[stage], a * 32, row0);
+        }
+        __syncwarp();
         if (++stage == p.num_stages) {
           stage = 0;
           phase ^= 1;
@@ -111,7 +118,7 @@ __global__ void __launch_bounds__(NCE_THREADS, 1) infonce_main_kernel(const __gr
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && t_end > t_begin) {
+    if (t_end > t_begin) {
       constexpr uint32_t idesc = make_idesc(UMMA_FMT_TF32, NCE_BM, NCE_BN);
       mbar_wait(q_full, 0);
       tc_fence_after_sync();
@@ -126,23 +133,24 @@ __global__ void __launch_bounds__(NCE_THREADS, 1) infonce_main_kernel(const __gr
         tc_fence_after_sync();
         const uint32_t st = smem_u32(stages + (size_t)stage * stage_bytes);
         const uint32_t d_tmem = tmem_base + acc * NCE_BN;
-        for (int a = 0; a < atoms; ++a) {
+        if (elect_one()) {
+          for (int a = 0; a < atoms; ++a) {
+            const uint64_t da0 = make_smem_desc(q_addr + a * NCE_BM * 128, 16, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t db0 = make_smem_desc(st + a * NCE_BN * 128, 16, 1024, UMMA_LAYOUT_SW128);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {          // 8 tf32 (32 bytes) per MMA
-            const uint64_t da = make_smem_desc(q_addr + a * NCE_BM * 128 + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-            const uint64_t db = make_smem_desc(st + a * NCE_BN * 128 + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-            umma_tf32(d_tmem, da, db, idesc, (a | k) != 0);
+            for (int k = 0; k < 4; ++k)            // 8 tf32 (32 bytes) per MMA: start address advances by 2 units
+              umma_tf32(d_tmem, da0 + 2 * k, db0 + 2 * k, idesc, (a | k) != 0);
           }
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&tmem_full[acc]);
         }
-        umma_commit(&empty_bar[stage]);
-        umma_commit(&tmem_full[acc]);
+        __syncwarp();
         if (++stage == p.num_stages) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
-    __syncwarp();
   } else {
     // ---- online softmax over negatives, one query row per thread ----
     const int quarter = warp & 3;
@@ -242,13 +250,12 @@ struct NceFinalizeParams {
   float* scalars;
 };
 
-__global__ void __launch_bounds__(1024, 1) infonce_finalize_kernel(const NceFinalizeParams p) {
-  __shared__ float red[5][32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarps = blockDim.x >> 5;
-  // per-warp running sums, accumulated in a fixed row order -> deterministic
-  float sum_dist = 0.f, sum_w = 0.f, sum_acc = 0.f, sum_pos = 0.f, sum_negmax = 0.f;
-  for (int i = warp; i < p.B; i += nwarps) {
+// one warp per query row; the five scalar means are produced afterwards by nce_scalars_kernel in a fixed order
+__global__ void __launch_bounds__(256) infonce_finalize_kernel(const NceFinalizeParams p) {
+  const int lane = threadIdx.x & 31;
+  {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= p.B) return;
     const int m_blk = i / NCE_BM, r = i % NCE_BM;
     // merge partials over slices (lanes stride over slices)
     float nmax = -INFINITY;
@@ -279,45 +286,26 @@ __global__ void __launch_bounds__(1024, 1) infonce_finalize_kernel(const NceFina
     }
     // Zneg relative to the row max over ALL columns (loss_util.py:24)
     const float Zn = (nmax == -INFINITY) ? 0.f : Z * expf(nmax / p.temperature - zmax);
-    float acc_i = 0.f, dist_i = 0.f, w_i = 0.f, pos_i = 0.f;
     for (int pp = 0; pp < p.nP; ++pp) {
       const float s = sig[pp] / p.temperature - zmax;
       const float logsm = s - logf(expf(s) + Zn);
-      const float dist = -logsm;
-      const float w = expf(logsm);
       if (lane == 0) {
-        p.dists[(size_t)i * p.nP + pp] = dist;
-        p.weights[(size_t)i * p.nP + pp] = w;
+        p.dists[(size_t)i * p.nP + pp] = -logsm;
+        p.weights[(size_t)i * p.nP + pp] = expf(logsm);
         p.pos_sim[(size_t)i * p.nP + pp] = sig[pp];
       }
-      dist_i += dist;
-      w_i += w;
-      pos_i += sig[pp];
-      acc_i += (sig[pp] > nmax) ? 1.f : 0.f;
     }
     if (lane == 0) {
       p.neg_max[i] = nmax;
       p.row_lse[2 * i] = zmax;
       p.row_lse[2 * i + 1] = Zn;
     }
-    sum_dist += dist_i;
-    sum_w += w_i;
-    sum_acc += acc_i;
-    sum_pos += pos_i;
-    sum_negmax += nmax;
-  }
-  if (lane == 0) {
-    red[0][warp] = sum_dist, red[1][warp] = sum_w, red[2][warp] = sum_acc, red[3][warp] = sum_pos;
-    red[4][warp] = sum_negmax;
-  }
-  __syncthreads();
-  if (threadIdx.x < 5) {
-    float s = 0.f;
-    for (int w = 0; w < nwarps; ++w) s += red[threadIdx.x][w];
-    const float denom = threadIdx.x == 4 ? (float)p.B : (float)p.B * (float)p.nP;
-    p.scalars[threadIdx.x] = s / denom;
   }
 }
+
+__global__ void nce_scalars_kernel(const float* __restrict__ dists, const float* __restrict__ weights,
+                                   const float* __restrict__ pos_sim, const float* __restrict__ neg_max, int R, int nP,
+                                   float* __restrict__ scalars);
 
 size_t infonce_workspace_bytes(int B, int D) {
   const size_t nmb = (B + NCE_BM - 1) / NCE_BM;
@@ -405,7 +393,9 @@ int infonce_fwd_launch(const InfoNceDesc& d, cudaStream_t stream) {
   fp.temperature = d.temperature, fp.scale_log2 = kp.scale_log2;
   fp.dists = d.dists, fp.weights = d.weights, fp.pos_sim = d.pos_sim, fp.neg_max = d.neg_max, fp.row_lse = d.row_lse;
   fp.scalars = d.scalars;
-  infonce_finalize_kernel<<<1, 1024, 0, stream>>>(fp);
+  infonce_finalize_kernel<<<(d.B + 7) / 8, 256, 0, stream>>>(fp);
+  VB_CHECK_CUDA(cudaGetLastError());
+  nce_scalars_kernel<<<1, 256, 0, stream>>>(d.dists, d.weights, d.pos_sim, d.neg_max, d.B, fp.nP, d.scalars);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }

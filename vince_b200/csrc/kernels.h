@@ -23,8 +23,23 @@ struct ConvGemmDesc {
   const float* bias;     // optional [N]
   int relu;
   double* stats;         // optional [2][N] (+=): per-channel sum and sum of squares of the raw outputs
+  int halo_mode;         // 3x3 stride-1 convs: -1 auto (use the shared-memory halo path when efficient), 0 off, 1 force
+  // optional train-mode BatchNorm finalize fused into the kernel tail (needs stats): the last CTA writes
+  // bn_coef[2][N] = (scale, shift) and updates the running statistics / num_batches_tracked
+  const float* bn_gamma;
+  const float* bn_beta;
+  float* bn_running_mean;
+  float* bn_running_var;
+  int64_t* bn_num_batches_tracked;
+  float* bn_coef;
+  unsigned int* bn_counter;   // must be 0 at launch
+  float bn_momentum, bn_eps;
+  void* trace;                // debug builds (-DVB_TRACE) only: [4][512] uint64 timeline of CTA 0
 };
 int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream);
+// eval-mode BatchNorm: coef[2][C] = (gamma / sqrt(running_var + eps), beta - running_mean * scale)
+int bn_eval_coef_launch(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, float* coef,
+                        int C, cudaStream_t stream);
 
 // ---- elementwise.cu -----------------------------------------------------------------------------
 // Stem input packing: NCHW fp32 image -> X[n, j, q, 64] bf16 hi/lo with
@@ -45,24 +60,19 @@ int weight_prep_launch(const WeightPrepEntry* table_dev, int n_entries, int64_t 
 
 struct BnSide {
   const float* raw;        // [M, C] raw conv output
-  const double* stats;     // [2][C] batch sums (train) or nullptr (eval: use running stats)
-  const float* gamma;
-  const float* beta;
-  float* running_mean;
-  float* running_var;
-  int64_t* num_batches_tracked;   // may be null
+  const float* coef;       // [2][C] per-channel (scale, shift) written by conv_gemm's fused finalize / bn_eval_coef
 };
 // out = relu?( bn(main) + residual ), residual = none | hi+lo planes | bn(second raw tensor)
 int bn_apply_launch(const BnSide& main, int res_kind, const __nv_bfloat16* res_hi, const __nv_bfloat16* res_lo,
                     const BnSide& res_bn, int relu, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, float* out_f32,
-                    int64_t M, int C, float momentum, float eps, cudaStream_t stream);
+                    int64_t M, int C, cudaStream_t stream);
 // stem: bn + relu + 3x3/2 pad-1 max pool, NHWC
 int bn_relu_maxpool_launch(const BnSide& bn, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int N, int P, int Q, int C,
-                           int P2, int Q2, float momentum, float eps, cudaStream_t stream);
+                           int P2, int Q2, cudaStream_t stream);
 // last block: relu(bn(main)+residual) -> NCHW fp32 spatial features (rows scattered by scatter_idx) + global mean
 int bn_final_pool_launch(const BnSide& main, int res_kind, const __nv_bfloat16* res_hi, const __nv_bfloat16* res_lo,
                          const BnSide& res_bn, const int64_t* scatter_idx, float* spatial_nchw, float* pooled, int N,
-                         int HW, int C, float momentum, float eps, cudaStream_t stream);
+                         int HW, int C, cudaStream_t stream);
 int split_bf16_launch(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t stream);
 int l2_normalize_launch(const float* x, float* out, int rows, int D, float eps, cudaStream_t stream);
 // NCHW fp32 [N,C,H,W] -> jigsaw patches NCHW [9N,C,H3,W3] (pad bottom/right with zeros to a multiple of 3)

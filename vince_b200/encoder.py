@@ -1,7 +1,9 @@
 """Host-side execution plan of the ResNet encoder forward on sm_100a kernels.
 
 `EncoderRunner` walks a torchvision-shaped ResNet parameter tree once, records one `ConvSpec` per convolution
-(where its prepared bf16 weights live, which BatchNorm follows it) and, per forward, issues
+(where its prepared bf16 weights live, which BatchNorm follows it) and, per input shape, builds a PLAN: a list of
+pre-marshalled kernel launches over a statically allocated activation arena (buffers are reused as soon as their
+last consumer has been issued).  Replaying a plan costs one ctypes call per kernel:
 
     weight_prep (1 launch, all tensors)  ->  stem_pack  ->  conv1 (im2col GEMM, +BN sums)  ->  bn+relu+maxpool
     -> per residual block:  conv (+sums) -> bn_apply(+relu) ... -> bn_apply(+residual, +relu)
@@ -52,10 +54,14 @@ class WeightBank:
         self.max_elems = max((s.Cout * s.K for s in specs), default=0)
         self.device = None
         self._ptrs = None
-        self.w_hi = self.w_lo = self.table = None
+        self.w_hi = self.w_lo = self.table = self._run = None
+        self.generation = 0            # bumps whenever the device buffers are re-created (plans must be rebuilt)
+
+    def key(self):
+        return tuple(s.weight.data_ptr() for s in self.specs)
 
     def _sync_device(self):
-        ptrs = tuple(s.weight.data_ptr() for s in self.specs)
+        ptrs = self.key()
         dev = self.specs[0].weight.device
         if dev.type != "cuda":
             raise RuntimeError("vince_b200: parameters live on %s; the encoder runs on CUDA only (no CPU fallback). "
@@ -72,11 +78,13 @@ class WeightBank:
         self.table = torch.from_numpy(arr.view(np.uint8).copy()).to(dev)
         self.w_hi = torch.empty((self.total,), device=dev, dtype=torch.bfloat16)
         self.w_lo = torch.empty((self.total,), device=dev, dtype=torch.bfloat16) if self.passes == 3 else None
+        self._run = ops.build_weight_prep(self.table, len(self.specs), self.max_elems, self.w_hi, self.w_lo)
         self._ptrs, self.device = ptrs, dev
+        self.generation += 1
 
     def refresh(self):
         self._sync_device()
-        ops.weight_prep(self.table, len(self.specs), self.max_elems, self.w_hi, self.w_lo)
+        self._run()
 
     def planes(self, spec):
         n = spec.Cout * spec.K
@@ -85,12 +93,51 @@ class WeightBank:
         return hi, lo
 
 
+class _Arena:
+    """Static activation allocator used while a plan is being built: a freed buffer is handed to the next request it
+    fits (best fit).  Safe because the plan always replays in the same order on one stream."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free_list = []         # (nbytes, tensor)
+        self.total = 0
+
+    def alloc(self, shape, dtype):
+        numel = 1
+        for s in shape:
+            numel *= s
+        nbytes = _align(max(numel, 1) * torch.empty((), dtype=dtype).element_size(), 512)
+        best = None
+        for i, (nb, _) in enumerate(self.free_list):
+            if nb >= nbytes and (best is None or nb < self.free_list[best][0]):
+                best = i
+        if best is not None and self.free_list[best][0] <= 2 * nbytes + (1 << 20):
+            nb, raw = self.free_list.pop(best)
+        else:
+            raw = torch.empty((nbytes,), device=self.device, dtype=torch.uint8)
+            nb = nbytes
+            self.total += nbytes
+        t = raw[:numel * torch.empty((), dtype=dtype).element_size()].view(dtype).view(shape)
+        t._arena_raw = (nb, raw)
+        return t
+
+    def free(self, *tensors):
+        for t in tensors:
+            if t is not None and hasattr(t, "_arena_raw"):
+                self.free_list.append(t._arena_raw)
+
+
 class Act:
     """NHWC activation as bf16 planes."""
     __slots__ = ("hi", "lo", "N", "H", "W", "C")
 
     def __init__(self, hi, lo, N, H, W, C):
         self.hi, self.lo, self.N, self.H, self.W, self.C = hi, lo, N, H, W, C
+
+
+class _Plan:
+    __slots__ = ("launches", "stats", "idx_gather", "idx_scatter", "x_hi", "x_lo", "final", "out_shape", "arena_bytes",
+                 "n_static")
 
 
 class EncoderRunner:
@@ -114,41 +161,135 @@ class EncoderRunner:
                     entry["down"] = ConvSpec(blk.downsample[0].weight, blk.downsample[1], blk.stride, 0)
                 specs += entry["convs"] + ([entry["down"]] if entry["down"] is not None else [])
                 self.blocks.append(entry)
+        # per conv, in one fp64 work buffer: [2*Cout] batch sums | [Cout] = 2*Cout fp32 (scale, shift) | [1] counter
         off = 0
         for s in specs:
             s.stats_off = off
-            off += 2 * s.Cout
+            off += 3 * s.Cout + 2        # (+1 pad: keeps every region 16-byte aligned for float4 coefficient loads)
         self.stats_total = off
         self.bank = WeightBank(specs, passes)
         self.launches = 0          # kernels launched by the last forward (bench bookkeeping)
+        self._plans = {}
+        self.block_n_override = None
+        import os
+        self.halo_mode = int(os.environ.get("VINCE_B200_HALO", "-1"))   # -1 auto, 0 off, 1 force (3x3 stride-1 convs)
+
+    def __deepcopy__(self, memo):
+        # plans hold raw device pointers of THIS model's parameters and arenas: a copy (VinceQueueModel deep-copies
+        # the encoder, vince_model.py:576) must start from the copied parameter tree with no cached plans
+        import copy
+        new = EncoderRunner(copy.deepcopy(self.model, memo), self.passes)
+        new.block_n_override = self.block_n_override
+        return new
 
     # ------------------------------------------------------------------------------------------
-    def _conv(self, act, spec, stats):
-        """raw fp32 [M, Cout] NHWC + batch sums.  Returns (raw, N, P, Q)."""
-        dev = act.hi.device
+    def _block_n(self, M, N):
+        if self.block_n_override is not None:
+            return self.block_n_override(M, N)
+        import os
+        if os.environ.get("VINCE_B200_BN256") == "1" and N % 256 == 0:
+            return 256
+        return 0
+
+    def _bn_args(self, spec, work, train):
+        """kwargs wiring conv_fwd's fused train-mode BN finalize for `spec` into the plan's work buffer"""
+        o, C = spec.stats_off, spec.Cout
+        if not train:
+            return {}
+        return dict(stats=work[o:o + 2 * C], bn=spec.bn, coef=work[o + 2 * C:o + 3 * C].view(torch.float32),
+                    counter=work[o + 3 * C:o + 3 * C + 1].view(torch.int32))
+
+    def _build_conv(self, arena, act, spec, work, train, launches):
         P = (act.H + 2 * spec.pad - spec.R) // spec.stride + 1
         Q = (act.W + 2 * spec.pad - spec.R) // spec.stride + 1
         M = act.N * P * Q
-        raw = torch.empty((M, spec.Cout), device=dev, dtype=torch.float32)
+        raw = arena.alloc((M, spec.Cout), torch.float32)
         w_hi, w_lo = self.bank.planes(spec)
-        st = stats[spec.stats_off:spec.stats_off + 2 * spec.Cout] if stats is not None else None
-        if spec.R == 1 and spec.stride == 1:
-            ops.conv_fwd(act.hi, act.lo, w_hi, w_lo, raw, M, spec.Cout, spec.K, passes=self.passes, stats=st)
-        else:
+        geom = None
+        if not (spec.R == 1 and spec.stride == 1):
             geom = dict(batch=act.N, H=act.H, W=act.W, Cin=act.C, R=spec.R, S=spec.R, stride=spec.stride,
                         pad_lo_h=spec.pad, pad_lo_w=spec.pad, pad_hi_h=spec.pad, pad_hi_w=spec.pad)
-            ops.conv_fwd(act.hi, act.lo, w_hi, w_lo, raw, M, spec.Cout, spec.K, passes=self.passes, geom=geom, stats=st)
-        self.launches += 1
+        launches.append(ops.build_conv_fwd(act.hi, act.lo, w_hi, w_lo, raw, M, spec.Cout, spec.K, passes=self.passes,
+                                           geom=geom, block_n=self._block_n(M, spec.Cout), halo_mode=self.halo_mode,
+                                           **self._bn_args(spec, work, train)))
         return raw, P, Q
 
-    def _planes(self, M, C, dev):
-        hi = torch.empty((M, C), device=dev, dtype=torch.bfloat16)
-        lo = torch.empty((M, C), device=dev, dtype=torch.bfloat16) if self.passes == 3 else None
+    def _planes(self, arena, M, C):
+        hi = arena.alloc((M, C), torch.bfloat16)
+        lo = arena.alloc((M, C), torch.bfloat16) if self.passes == 3 else None
         return hi, lo
 
-    def _side(self, raw, spec, stats):
-        st = stats[spec.stats_off:spec.stats_off + 2 * spec.Cout] if stats is not None else None
-        return ops.bn_side(raw, st, spec.bn)
+    def _side(self, raw, spec, work):
+        o, C = spec.stats_off, spec.Cout
+        return ops.bn_side(raw, work[o + 2 * C:o + 3 * C].view(torch.float32))
+
+    def _build_plan(self, N, H, W, train, dev):
+        plan = _Plan()
+        arena = _Arena(dev)
+        launches = []
+        # BN work buffer (sums, coefficients, finalize counters); zeroed once per train-mode forward
+        stats = work = torch.zeros((self.stats_total,), device=dev, dtype=torch.float64)
+        plan.stats = work
+        if not train:
+            # eval-mode BatchNorm: coefficients from the running statistics, one tiny launch per BN layer
+            for spec in self.bank.specs:
+                o, C = spec.stats_off, spec.Cout
+                launches.append(ops.build_bn_eval_coef(spec.bn, work[o + 2 * C:o + 3 * C].view(torch.float32)))
+        plan.idx_gather = torch.zeros((N,), device=dev, dtype=torch.int64)
+        plan.idx_scatter = torch.zeros((N,), device=dev, dtype=torch.int64)
+        # ---- stem (stem_pack itself is bound per call: it reads the caller's tensor) ----
+        sg = ops.stem_geometry(H, W)
+        P, Q, Hj = sg["P"], sg["Q"], sg["Hj"]
+        plan.x_hi = arena.alloc((N, Hj, Q, 64), torch.bfloat16)
+        plan.x_lo = arena.alloc((N, Hj, Q, 64), torch.bfloat16) if self.passes == 3 else None
+        w_hi, w_lo = self.bank.planes(self.stem)
+        M = N * P * Q
+        raw = arena.alloc((M, 64), torch.float32)
+        launches.append(ops.build_conv_fwd(plan.x_hi, plan.x_lo, w_hi, w_lo, raw, M, 64, 256, passes=self.passes,
+                                           geom=dict(sg["geom"], batch=N), **self._bn_args(self.stem, work, train)))
+        arena.free(plan.x_hi, plan.x_lo)
+        P2, Q2 = (P - 1) // 2 + 1, (Q - 1) // 2 + 1
+        hi, lo = self._planes(arena, N * P2 * Q2, 64)
+        launches.append(ops.build_bn_relu_maxpool(self._side(raw, self.stem, stats), hi, lo, N, P, Q, 64))
+        arena.free(raw)
+        act = Act(hi, lo, N, P2, Q2, 64)
+        # ---- residual blocks ----
+        for bi, blk in enumerate(self.blocks):
+            last = bi == len(self.blocks) - 1
+            cur = act
+            convs = blk["convs"]
+            for spec in convs[:-1]:
+                raw, p_, q_ = self._build_conv(arena, cur, spec, work, train, launches)
+                hi, lo = self._planes(arena, raw.shape[0], spec.Cout)
+                launches.append(ops.build_bn_apply(self._side(raw, spec, stats), raw.shape[0], spec.Cout, True, hi, lo))
+                arena.free(raw)
+                if cur is not act:
+                    arena.free(cur.hi, cur.lo)
+                cur = Act(hi, lo, cur.N, p_, q_, spec.Cout)
+            spec = convs[-1]
+            raw, p_, q_ = self._build_conv(arena, cur, spec, work, train, launches)
+            if cur is not act:
+                arena.free(cur.hi, cur.lo)
+            kw = {}
+            raw_ds = None
+            if blk["down"] is not None:
+                raw_ds, _, _ = self._build_conv(arena, act, blk["down"], work, train, launches)
+                kw["res_bn"] = self._side(raw_ds, blk["down"], stats)
+            else:
+                kw["res_planes"] = (act.hi, act.lo)
+            main = self._side(raw, spec, stats)
+            if last:
+                plan.final = dict(main=main, N=N, HW=p_ * q_, C=spec.Cout, kw=kw, keep=(raw, raw_ds, act))
+                plan.out_shape = (N, spec.Cout, p_, q_)
+            else:
+                hi, lo = self._planes(arena, raw.shape[0], spec.Cout)
+                launches.append(ops.build_bn_apply(main, raw.shape[0], spec.Cout, True, hi, lo, **kw))
+                arena.free(raw, raw_ds, act.hi, act.lo)
+                act = Act(hi, lo, N, p_, q_, spec.Cout)
+        plan.launches = launches
+        plan.arena_bytes = arena.total
+        plan.n_static = len(launches)
+        return plan
 
     # ------------------------------------------------------------------------------------------
     def forward(self, x, train, gather_idx=None, scatter_idx=None, want_spatial=True):
@@ -160,63 +301,34 @@ class EncoderRunner:
         x = x.contiguous()
         dev = x.device
         N, C3, H, W = x.shape
-        self.launches = 0
         with torch.cuda.device(dev):
             self.bank.refresh()
-            self.launches += 1
-            stats = None
+            key = (N, H, W, bool(train), dev.index, self.bank.generation)
+            if self._plans and next(iter(self._plans))[-1] != self.bank.generation:
+                self._plans.clear()                         # parameters moved: every cached pointer is stale
+            plan = self._plans.get(key)
+            if plan is None:
+                if len(self._plans) >= 4:                   # bound the number of resident activation arenas
+                    self._plans.pop(next(iter(self._plans)))
+                plan = self._build_plan(N, H, W, bool(train), dev)
+                self._plans[key] = plan
             if train:
-                stats = torch.zeros((self.stats_total,), device=dev, dtype=torch.float64)
-            # ---- stem ----
-            sg = ops.stem_geometry(H, W)
-            P, Q, Hj = sg["P"], sg["Q"], sg["Hj"]
-            x_hi = torch.empty((N, Hj, Q, 64), device=dev, dtype=torch.bfloat16)
-            x_lo = torch.empty_like(x_hi) if self.passes == 3 else None
-            ops.stem_pack(x, gather_idx, x_hi, x_lo)
-            w_hi, w_lo = self.bank.planes(self.stem)
-            M = N * P * Q
-            raw = torch.empty((M, 64), device=dev, dtype=torch.float32)
-            st = stats[self.stem.stats_off:self.stem.stats_off + 128] if train else None
-            ops.conv_fwd(x_hi, x_lo, w_hi, w_lo, raw, M, 64, 256, passes=self.passes, geom=dict(sg["geom"], batch=N),
-                         stats=st)
-            del x_hi, x_lo
-            P2, Q2 = (P - 1) // 2 + 1, (Q - 1) // 2 + 1
-            hi, lo = self._planes(N * P2 * Q2, 64, dev)
-            ops.bn_relu_maxpool(self._side(raw, self.stem, stats), hi, lo, N, P, Q, 64)
-            self.launches += 3
-            act = Act(hi, lo, N, P2, Q2, 64)
-            del raw
-            # ---- residual blocks ----
-            spatial = pooled = None
-            for bi, blk in enumerate(self.blocks):
-                last = bi == len(self.blocks) - 1
-                cur = act
-                convs = blk["convs"]
-                for ci, spec in enumerate(convs[:-1]):
-                    raw, p_, q_ = self._conv(cur, spec, stats)
-                    hi, lo = self._planes(raw.shape[0], spec.Cout, dev)
-                    ops.bn_apply(self._side(raw, spec, stats), raw.shape[0], spec.Cout, True, hi, lo)
-                    self.launches += 1
-                    cur = Act(hi, lo, cur.N, p_, q_, spec.Cout)
-                spec = convs[-1]
-                raw, p_, q_ = self._conv(cur, spec, stats)
-                kw = {}
-                if blk["down"] is not None:
-                    raw_ds, _, _ = self._conv(act, blk["down"], stats)
-                    kw["res_bn"] = self._side(raw_ds, blk["down"], stats)
-                else:
-                    kw["res_planes"] = (act.hi, act.lo)
-                main = self._side(raw, spec, stats)
-                if last:
-                    C = spec.Cout
-                    spatial = torch.empty((N, C, p_, q_), device=dev, dtype=torch.float32) if want_spatial else None
-                    pooled = torch.empty((N, C), device=dev, dtype=torch.float32)
-                    ops.bn_final_pool(main, N, p_ * q_, C, spatial, pooled, scatter_idx=scatter_idx, **kw)
-                else:
-                    hi, lo = self._planes(raw.shape[0], spec.Cout, dev)
-                    ops.bn_apply(main, raw.shape[0], spec.Cout, True, hi, lo, **kw)
-                    act = Act(hi, lo, N, p_, q_, spec.Cout)
-                self.launches += 1
+                plan.stats.zero_()
+            gi = si = None
+            if gather_idx is not None:
+                plan.idx_gather.copy_(gather_idx)
+                gi = plan.idx_gather
+            if scatter_idx is not None:
+                plan.idx_scatter.copy_(scatter_idx)
+                si = plan.idx_scatter
+            ops.build_stem_pack(x, gi, plan.x_hi, plan.x_lo)()
+            for run in plan.launches:
+                run()
+            f = plan.final
+            spatial = torch.empty(plan.out_shape, device=dev, dtype=torch.float32) if want_spatial else None
+            pooled = torch.empty((N, f["C"]), device=dev, dtype=torch.float32)
+            ops.build_bn_final_pool(f["main"], f["N"], f["HW"], f["C"], spatial, pooled, scatter_idx=si, **f["kw"])()
+            self.launches = plan.n_static + 3 + (1 if train else 0)       # + weight_prep, stem_pack, final (+ memset)
         return spatial, pooled
 
 
@@ -230,6 +342,10 @@ class HeadRunner:
         self.specs = [ConvSpec(l.weight, None, 1, 0, bias=l.bias) for l in self.linears]
         self.bank = WeightBank(self.specs, passes)
         self.launches = 0
+
+    def __deepcopy__(self, memo):
+        import copy
+        return HeadRunner(copy.deepcopy(self.linears, memo), self.passes)
 
     def refresh(self):
         self.bank.refresh()

@@ -1,5 +1,10 @@
 """Tensor-level wrappers over the C ABI: validate (device / dtype / contiguity / shape) in Python, pass raw device
-pointers + the current CUDA stream.  No op has a CPU or PyTorch fallback - non-CUDA tensors raise."""
+pointers + the current CUDA stream.  No op has a CPU or PyTorch fallback - non-CUDA tensors raise.
+
+Every op exists in two forms: `build_<op>(...)` validates once and returns a zero-argument callable with all ctypes
+arguments pre-marshalled (the encoder plan replays lists of these, so the per-launch host cost is one ctypes call),
+and `<op>(...)` = build + run for one-off use.
+"""
 import ctypes
 
 import torch
@@ -30,30 +35,50 @@ def _ptr(t, dtype=None, name="tensor"):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def bn_side(raw, stats, bn):
-    """bn: object with .weight .bias .running_mean .running_var .num_batches_tracked tensors.
-    stats=None selects eval mode (running statistics)."""
+def _val(t, dtype, name):
+    p = _ptr(t, dtype, name)
+    return p.value if p is not None else None
+
+
+def _bind(fn, what, *args):
+    """Callable that launches fn(*args, current_stream) and raises on a non-zero status."""
+    check = _lib.check
+
+    def run():
+        check(fn(*args, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), what)
+    return run
+
+
+def bn_side(raw, coef):
+    """raw: [M,C] fp32 conv output; coef: [2*C] fp32 (scale, shift) from the conv's fused BN finalize or bn_eval_coef."""
     s = _lib.BnSide()
-    s.raw = _ptr(raw, torch.float32, "bn.raw").value
-    s.stats = _ptr(stats, torch.float64, "bn.stats").value if stats is not None else None
-    s.gamma = _ptr(bn.weight, torch.float32, "bn.weight").value
-    s.beta = _ptr(bn.bias, torch.float32, "bn.bias").value
-    s.running_mean = _ptr(bn.running_mean, torch.float32, "bn.running_mean").value
-    s.running_var = _ptr(bn.running_var, torch.float32, "bn.running_var").value
-    nbt = getattr(bn, "num_batches_tracked", None)
-    s.num_batches_tracked = _ptr(nbt, torch.int64, "bn.num_batches_tracked").value if nbt is not None else None
+    s.raw = _val(raw, torch.float32, "bn.raw")
+    s.coef = _val(coef, torch.float32, "bn.coef")
+    s._keep = (raw, coef)
     return s
 
 
-def conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, block_n=0, scale=None, bias=None, relu=False,
-             stats=None):
-    """geom=None: A is [M,K]; else dict(batch,H,W,Cin,R,S,stride,pad_lo_h,pad_lo_w,pad_hi_h,pad_hi_w) (NHWC gather)."""
+def build_bn_eval_coef(bn, coef):
+    """eval-mode BatchNorm: coef <- (gamma / sqrt(running_var + eps), beta - running_mean * scale)"""
+    C = bn.weight.numel()
+    run = _bind(_lib.lib().vince_bn_eval_coef, "vince_bn_eval_coef", _ptr(bn.weight, torch.float32, "bn.weight"),
+                _ptr(bn.bias, torch.float32, "bn.bias"), _ptr(bn.running_mean, torch.float32, "bn.running_mean"),
+                _ptr(bn.running_var, torch.float32, "bn.running_var"), BN_EPS, _ptr(coef, torch.float32, "coef"), C)
+    run._keep = (bn, coef)
+    return run
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def build_conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, block_n=0, scale=None, bias=None,
+                   relu=False, stats=None, bn=None, coef=None, counter=None, halo_mode=-1):
+    """geom=None: A is [M,K]; else dict(batch,H,W,Cin,R,S,stride,pad_lo_h,pad_lo_w,pad_hi_h,pad_hi_w) (NHWC gather).
+    bn/coef/counter (with stats): fuse the train-mode BatchNorm finalize of module `bn` into the kernel tail."""
     d = _lib.ConvDesc()
-    d.a_hi = _ptr(a_hi, torch.bfloat16, "a_hi").value
-    d.a_lo = _ptr(a_lo, torch.bfloat16, "a_lo").value if a_lo is not None else None
-    d.w_hi = _ptr(w_hi, torch.bfloat16, "w_hi").value
-    d.w_lo = _ptr(w_lo, torch.bfloat16, "w_lo").value if w_lo is not None else None
-    d.out = _ptr(out, torch.float32, "out").value
+    d.a_hi = _val(a_hi, torch.bfloat16, "a_hi")
+    d.a_lo = _val(a_lo, torch.bfloat16, "a_lo")
+    d.w_hi = _val(w_hi, torch.bfloat16, "w_hi")
+    d.w_lo = _val(w_lo, torch.bfloat16, "w_lo")
+    d.out = _val(out, torch.float32, "out")
     if out.numel() < M * N:
         raise ValueError("conv_fwd: output buffer too small")
     d.M, d.N, d.K = M, N, K
@@ -63,20 +88,44 @@ def conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, block_n=
             setattr(d, k, int(geom[k]))
     d.passes = passes
     d.block_n = block_n
-    d.scale = _ptr(scale, torch.float32, "scale").value if scale is not None else None
-    d.bias = _ptr(bias, torch.float32, "bias").value if bias is not None else None
+    d.scale = _val(scale, torch.float32, "scale")
+    d.bias = _val(bias, torch.float32, "bias")
     d.relu = 1 if relu else 0
-    d.stats = _ptr(stats, torch.float64, "stats").value if stats is not None else None
-    if PROFILE is not None:
-        # bench.py's roofline leg: CUDA events around every tensor-core launch, on the launching stream
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _lib.check(_lib.lib().vince_conv_fwd(ctypes.byref(d), _stream()), "vince_conv_fwd")
-        e1.record()
-        k_true = geom.get("K_true", K) if geom is not None else K
-        PROFILE.append(("conv_gemm", 2.0 * M * N * k_true, e0, e1))
-        return
-    _lib.check(_lib.lib().vince_conv_fwd(ctypes.byref(d), _stream()), "vince_conv_fwd")
+    d.stats = _val(stats, torch.float64, "stats")
+    d.halo_mode = halo_mode
+    if bn is not None:
+        if stats is None or coef is None or counter is None:
+            raise ValueError("conv_fwd: the fused BatchNorm finalize needs stats, coef and counter buffers")
+        d.bn_gamma = _val(bn.weight, torch.float32, "bn.weight")
+        d.bn_beta = _val(bn.bias, torch.float32, "bn.bias")
+        d.bn_running_mean = _val(bn.running_mean, torch.float32, "bn.running_mean")
+        d.bn_running_var = _val(bn.running_var, torch.float32, "bn.running_var")
+        d.bn_num_batches_tracked = _val(getattr(bn, "num_batches_tracked", None), torch.int64, "bn.num_batches_tracked")
+        d.bn_coef = _val(coef, torch.float32, "coef")
+        d.bn_counter = _val(counter, torch.int32, "counter")
+        d.bn_momentum, d.bn_eps = BN_MOMENTUM, BN_EPS
+    fn = _lib.lib().vince_conv_fwd
+    ref = ctypes.byref(d)
+    flops = 2.0 * M * N * (geom.get("K_true", K) if geom is not None else K)
+    check = _lib.check
+
+    def run():
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if PROFILE is not None:
+            # bench.py's roofline leg: CUDA events around every tensor-core launch, on the launching stream
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            check(fn(ref, stream), "vince_conv_fwd")
+            e1.record()
+            PROFILE.append(("conv_gemm", flops, e0, e1))
+        else:
+            check(fn(ref, stream), "vince_conv_fwd")
+    run._keep = (d, a_hi, a_lo, w_hi, w_lo, out, scale, bias, stats, bn, coef, counter)
+    return run
+
+
+def conv_fwd(*a, **k):
+    build_conv_fwd(*a, **k)()
 
 
 def stem_geometry(H, W):
@@ -88,55 +137,86 @@ def stem_geometry(H, W):
                           pad_hi_w=0, K_true=147))      # algorithmic K of the 7x7x3 stem (the packed K is 256)
 
 
-def stem_pack(x, gather_idx, x_hi, x_lo):
+def build_stem_pack(x, gather_idx, x_hi, x_lo):
     N, C, H, W = x.shape
     if C != 3:
         raise ValueError("stem_pack: expected 3 input channels")
-    _lib.check(_lib.lib().vince_stem_pack(_ptr(x, torch.float32, "x"), _ptr(gather_idx, torch.int64, "gather_idx"),
-                                         _ptr(x_hi, torch.bfloat16, "x_hi"), _ptr(x_lo, torch.bfloat16, "x_lo"),
-                                         N, H, W, _stream()), "vince_stem_pack")
+    run = _bind(_lib.lib().vince_stem_pack, "vince_stem_pack", _ptr(x, torch.float32, "x"),
+                _ptr(gather_idx, torch.int64, "gather_idx"), _ptr(x_hi, torch.bfloat16, "x_hi"),
+                _ptr(x_lo, torch.bfloat16, "x_lo"), N, H, W)
+    run._keep = (x, gather_idx, x_hi, x_lo)
+    return run
 
 
-def weight_prep(table_dev, n_entries, max_elems, w_hi, w_lo):
-    _lib.check(_lib.lib().vince_weight_prep(_ptr(table_dev, torch.uint8, "table"), n_entries, max_elems,
-                                           _ptr(w_hi, torch.bfloat16, "w_hi"), _ptr(w_lo, torch.bfloat16, "w_lo"),
-                                           _stream()), "vince_weight_prep")
+def stem_pack(*a):
+    build_stem_pack(*a)()
 
 
-def bn_apply(main, M, C, relu, out_hi=None, out_lo=None, out_f32=None, res_planes=None, res_bn=None):
-    res_kind, rh, rl, rb = 0, None, None, None
+def build_weight_prep(table_dev, n_entries, max_elems, w_hi, w_lo):
+    run = _bind(_lib.lib().vince_weight_prep, "vince_weight_prep", _ptr(table_dev, torch.uint8, "table"), n_entries,
+                max_elems, _ptr(w_hi, torch.bfloat16, "w_hi"), _ptr(w_lo, torch.bfloat16, "w_lo"))
+    run._keep = (table_dev, w_hi, w_lo)
+    return run
+
+
+def weight_prep(*a):
+    build_weight_prep(*a)()
+
+
+def _residual(res_planes, res_bn):
     if res_planes is not None:
-        res_kind, rh, rl = 1, _ptr(res_planes[0], torch.bfloat16, "res_hi"), _ptr(res_planes[1], torch.bfloat16, "res_lo")
-    elif res_bn is not None:
-        res_kind, rb = 2, ctypes.byref(res_bn)
-    _lib.check(_lib.lib().vince_bn_apply(ctypes.byref(main), res_kind, rh, rl, rb, 1 if relu else 0,
-                                        _ptr(out_hi, torch.bfloat16, "out_hi"), _ptr(out_lo, torch.bfloat16, "out_lo"),
-                                        _ptr(out_f32, torch.float32, "out_f32"), M, C, BN_MOMENTUM, BN_EPS, _stream()),
-               "vince_bn_apply")
+        return 1, _ptr(res_planes[0], torch.bfloat16, "res_hi"), _ptr(res_planes[1], torch.bfloat16, "res_lo"), None
+    if res_bn is not None:
+        return 2, None, None, ctypes.byref(res_bn)
+    return 0, None, None, None
 
 
-def bn_relu_maxpool(bn, out_hi, out_lo, N, P, Q, C):
-    _lib.check(_lib.lib().vince_bn_relu_maxpool(ctypes.byref(bn), _ptr(out_hi, torch.bfloat16, "out_hi"),
-                                               _ptr(out_lo, torch.bfloat16, "out_lo"), N, P, Q, C, BN_MOMENTUM, BN_EPS,
-                                               _stream()), "vince_bn_relu_maxpool")
+def build_bn_apply(main, M, C, relu, out_hi=None, out_lo=None, out_f32=None, res_planes=None, res_bn=None):
+    res_kind, rh, rl, rb = _residual(res_planes, res_bn)
+    run = _bind(_lib.lib().vince_bn_apply, "vince_bn_apply", ctypes.byref(main), res_kind, rh, rl, rb,
+                1 if relu else 0, _ptr(out_hi, torch.bfloat16, "out_hi"), _ptr(out_lo, torch.bfloat16, "out_lo"),
+                _ptr(out_f32, torch.float32, "out_f32"), M, C)
+    run._keep = (main, res_planes, res_bn, out_hi, out_lo, out_f32)
+    return run
 
 
-def bn_final_pool(main, N, HW, C, spatial_nchw, pooled, scatter_idx=None, res_planes=None, res_bn=None):
-    res_kind, rh, rl, rb = 0, None, None, None
-    if res_planes is not None:
-        res_kind, rh, rl = 1, _ptr(res_planes[0], torch.bfloat16, "res_hi"), _ptr(res_planes[1], torch.bfloat16, "res_lo")
-    elif res_bn is not None:
-        res_kind, rb = 2, ctypes.byref(res_bn)
-    _lib.check(_lib.lib().vince_bn_final_pool(ctypes.byref(main), res_kind, rh, rl, rb,
-                                             _ptr(scatter_idx, torch.int64, "scatter_idx"),
-                                             _ptr(spatial_nchw, torch.float32, "spatial"),
-                                             _ptr(pooled, torch.float32, "pooled"), N, HW, C, BN_MOMENTUM, BN_EPS,
-                                             _stream()), "vince_bn_final_pool")
+def bn_apply(*a, **k):
+    build_bn_apply(*a, **k)()
 
 
-def split_bf16(x, hi, lo):
-    _lib.check(_lib.lib().vince_split_bf16(_ptr(x, torch.float32, "x"), _ptr(hi, torch.bfloat16, "hi"),
-                                          _ptr(lo, torch.bfloat16, "lo"), x.numel(), _stream()), "vince_split_bf16")
+def build_bn_relu_maxpool(bn, out_hi, out_lo, N, P, Q, C):
+    run = _bind(_lib.lib().vince_bn_relu_maxpool, "vince_bn_relu_maxpool", ctypes.byref(bn),
+                _ptr(out_hi, torch.bfloat16, "out_hi"), _ptr(out_lo, torch.bfloat16, "out_lo"), N, P, Q, C)
+    run._keep = (bn, out_hi, out_lo)
+    return run
+
+
+def bn_relu_maxpool(*a):
+    build_bn_relu_maxpool(*a)()
+
+
+def build_bn_final_pool(main, N, HW, C, spatial_nchw, pooled, scatter_idx=None, res_planes=None, res_bn=None):
+    res_kind, rh, rl, rb = _residual(res_planes, res_bn)
+    run = _bind(_lib.lib().vince_bn_final_pool, "vince_bn_final_pool", ctypes.byref(main), res_kind, rh, rl, rb,
+                _ptr(scatter_idx, torch.int64, "scatter_idx"), _ptr(spatial_nchw, torch.float32, "spatial"),
+                _ptr(pooled, torch.float32, "pooled"), N, HW, C)
+    run._keep = (main, res_planes, res_bn, scatter_idx, spatial_nchw, pooled)
+    return run
+
+
+def bn_final_pool(*a, **k):
+    build_bn_final_pool(*a, **k)()
+
+
+def build_split_bf16(x, hi, lo):
+    run = _bind(_lib.lib().vince_split_bf16, "vince_split_bf16", _ptr(x, torch.float32, "x"),
+                _ptr(hi, torch.bfloat16, "hi"), _ptr(lo, torch.bfloat16, "lo"), x.numel())
+    run._keep = (x, hi, lo)
+    return run
+
+
+def split_bf16(*a):
+    build_split_bf16(*a)()
 
 
 def round_tf32(x, out):
@@ -144,10 +224,16 @@ def round_tf32(x, out):
                                           _stream()), "vince_round_tf32")
 
 
-def l2_normalize(x, out, eps=1e-12):
+def build_l2_normalize(x, out, eps=1e-12):
     rows, D = x.shape
-    _lib.check(_lib.lib().vince_l2_normalize(_ptr(x, torch.float32, "x"), _ptr(out, torch.float32, "out"), rows, D, eps,
-                                            _stream()), "vince_l2_normalize")
+    run = _bind(_lib.lib().vince_l2_normalize, "vince_l2_normalize", _ptr(x, torch.float32, "x"),
+                _ptr(out, torch.float32, "out"), rows, D, eps)
+    run._keep = (x, out)
+    return run
+
+
+def l2_normalize(*a, **k):
+    build_l2_normalize(*a, **k)()
 
 
 def jigsaw_patchify(x, gather_idx, out):
@@ -175,25 +261,28 @@ def infonce_fwd(q, keys, queue_tf32, num_frames, temperature, workspace=None):
     K = 0 if queue_tf32 is None else queue_tf32.shape[0]
     nP = num_frames if num_frames > 0 else 1
     dev = q.device
-    out = {
-        "dists": torch.empty((B, nP), device=dev, dtype=torch.float32),
-        "weights": torch.empty((B, nP), device=dev, dtype=torch.float32),
-        "pos_sim": torch.empty((B, nP), device=dev, dtype=torch.float32),
-        "neg_max": torch.empty((B,), device=dev, dtype=torch.float32),
-        "row_lse": torch.empty((B, 2), device=dev, dtype=torch.float32),
-        "scalars": torch.zeros((8,), device=dev, dtype=torch.float32),
-    }
+    # one allocation for all per-row outputs (a single caching-allocator call on the hot path)
+    buf = torch.empty((B * (3 * nP + 3) + 8,), device=dev, dtype=torch.float32)
+    o = 0
+    out = {}
+    for name, shape in (("dists", (B, nP)), ("weights", (B, nP)), ("pos_sim", (B, nP)), ("neg_max", (B,)),
+                        ("row_lse", (B, 2)), ("scalars", (8,))):
+        n = 1
+        for s in shape:
+            n *= s
+        out[name] = buf[o:o + n].view(shape)
+        o += n
     if workspace is None:
         workspace = torch.empty((infonce_workspace_bytes(B, D),), device=dev, dtype=torch.uint8)
     d = _lib.InfoNceDesc()
-    d.q = _ptr(q, torch.float32, "q").value
-    d.keys = _ptr(keys, torch.float32, "keys").value
-    d.queue_tf32 = _ptr(queue_tf32, torch.float32, "queue_tf32").value if K > 0 else None
+    d.q = _val(q, torch.float32, "q")
+    d.keys = _val(keys, torch.float32, "keys")
+    d.queue_tf32 = _val(queue_tf32, torch.float32, "queue_tf32") if K > 0 else None
     d.B, d.Bk, d.K, d.D, d.num_frames = B, keys.shape[0], K, D, num_frames
     d.temperature = float(temperature)
     for k in ("dists", "weights", "pos_sim", "neg_max", "row_lse", "scalars"):
         setattr(d, k, out[k].data_ptr())
-    d.workspace = _ptr(workspace, torch.uint8, "workspace").value
+    d.workspace = _val(workspace, torch.uint8, "workspace")
     _lib.check(_lib.lib().vince_infonce_fwd(ctypes.byref(d), _stream()), "vince_infonce_fwd")
     out["_workspace"] = workspace     # keep alive until the stream has consumed it
     return out
