@@ -1,0 +1,149 @@
+"""CPU: the C-ABI library loads and exports every symbol include/vince_b200.h declares (no compute calls), argument
+validation fails loudly, and the host-side logic (plans, ring arithmetic, API shapes) behaves like the reference."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import vince_oracle as vo
+from conftest import ROOT, make_args
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "vince_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vince_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from vince_b200 import _lib
+    dll = _lib.lib()
+    names = declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(dll, n), "missing export: " + n
+    assert set(names) == set(_lib.SIGNATURES), (set(names) ^ set(_lib.SIGNATURES))
+    assert dll.vince_abi_version() == 1
+    assert int(dll.vince_infonce_workspace_bytes(256, 128)) > 2 * 256 * 128 * 4
+
+
+def test_struct_layouts_match_the_header():
+    """sizes that nvcc's static_asserts also pin on the C side"""
+    from vince_b200 import _lib
+    assert ctypes.sizeof(_lib.BnSide) == 16
+    assert ctypes.sizeof(_lib.ConvDesc) % 8 == 0 and ctypes.sizeof(_lib.ConvDesc) >= 200
+    assert _lib.ConvDesc.stats.offset % 8 == 0 and _lib.ConvDesc.bn_counter.offset % 8 == 0
+
+
+def test_argument_validation_fails_loudly_without_touching_the_gpu():
+    from vince_b200 import _lib
+    dll = _lib.lib()
+    d = _lib.ConvDesc()
+    assert dll.vince_conv_fwd(ctypes.byref(d), None) == -1
+    assert "empty problem" in _lib.last_error()
+    assert dll.vince_conv_fwd(None, None) == -1
+    n = _lib.InfoNceDesc()
+    assert dll.vince_infonce_fwd(ctypes.byref(n), None) == -1
+    assert dll.vince_stem_pack(None, None, None, None, 1, 8, 8, None) == -1
+    with pytest.raises(RuntimeError):
+        _lib.check(-1, "x")
+
+
+def test_ops_reject_cpu_tensors_and_missing_library():
+    from vince_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.l2_normalize(torch.zeros(4, 8), torch.zeros(4, 8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.round_tf32(torch.zeros(4), torch.zeros(4))
+    code = ("import os,sys; sys.path.insert(0, %r); os.environ['VINCE_B200_LIB']='/nonexistent/lib.so';"
+            "from vince_b200 import _lib\ntry:\n    _lib.lib()\nexcept RuntimeError as e:\n    print('RAISED', 'no CPU' in str(e))" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert "RAISED True" in out.stdout, out.stdout + out.stderr
+
+
+def test_model_refuses_cpu_inputs_and_cpu_parameters():
+    import vince_b200
+    args = make_args(batch_size=4, num_frames=2, queue_size=16, embedding_size=32, device="cuda:0")
+    m = vince_b200.VinceModel(args)
+    with pytest.raises(RuntimeError, match="GPU"):
+        m.get_embeddings({"data": torch.zeros(4, 3, 32, 32)})
+    with pytest.raises(RuntimeError):
+        vince_b200.StorageQueue(16, 32, device="cpu")
+
+
+@pytest.mark.parametrize("backbone,n_convs,n_params", [("ResNet18", 20, 12017832), ("ResNet50", 53, 30015656)])
+def test_parameter_tree_matches_the_reference(backbone, n_convs, n_params):
+    import vince_b200
+    args = make_args(backbone=backbone, batch_size=8, num_frames=2, queue_size=64, embedding_size=128, device="cpu")
+    m = vince_b200.VinceModel(args)
+    sd = vo.make_state_dict(backbone, 128)                 # key names / shapes of the reference's state_dict
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    assert all(m.state_dict()[k].shape == sd[k].shape for k in sd)
+    assert sum(p.numel() for p in m.vince_parameters()) == n_params      # a10
+    runner = m.feature_extractor.module.runner
+    assert len(runner.bank.specs) == n_convs
+    assert m.output_channels == (512 if backbone == "ResNet18" else 2048)
+    assert m.to("cpu") is None                             # reference quirk: .to() returns None (vince_model.py:92-94)
+    # deep copy (VinceQueueModel) re-binds the runner to the copied parameters and freezes them
+    qm = vince_b200.VinceQueueModel(args, m)
+    r2 = qm.queue_network.feature_extractor.module.runner
+    assert r2 is not runner and r2.stem.weight is qm.queue_network.feature_extractor.module.model.conv1.weight
+    assert all(not p.requires_grad for p in qm.queue_network.parameters())
+    assert len(qm.queue_network.vince_parameters()) == len(m.vince_parameters())
+
+
+def test_split_dict_by_type_semantics():
+    import vince_b200
+    d = {"a": torch.arange(10), "b": torch.arange(20).view(10, 2)}
+    out = vince_b200.VinceModel.split_dict_by_type(["x", "y"], [4, 6], d)
+    assert [o["batch_type"] for o in out] == ["x", "y"]
+    assert out[0]["a"].tolist() == [0, 1, 2, 3] and out[1]["b"].shape == (6, 2)
+    one = vince_b200.VinceModel.split_dict_by_type(["images"], [10], d)
+    assert one[0]["a"].shape == (10,) and "batch_types" not in one[0]
+
+
+def test_stem_geometry_and_ring_slices():
+    from vince_b200 import ops
+    from vince_b200.distributed import ring_slices
+    for H in (224, 225, 75, 64, 51):
+        sg = ops.stem_geometry(H, H)
+        P = (H + 6 - 7) // 2 + 1
+        assert sg["P"] == P and sg["Hj"] == H // 2 + 1
+        g = sg["geom"]
+        assert (g["H"] + g["pad_lo_h"] + g["pad_hi_h"] - g["R"]) // g["stride"] + 1 == P and g["pad_hi_h"] >= 0
+    rng = np.random.RandomState(0)
+    for _ in range(200):
+        K = int(rng.randint(1, 40))
+        q = vo.StorageQueue(K, 1, init=torch.zeros(K, 1))
+        tail = 0
+        for step in range(12):
+            n = int(rng.randint(0, K + 1))
+            items = torch.full((n, 1), float(step + 1))
+            ref_before = q.vector_queue.clone()
+            q.enqueue(items)
+            slices, new_tail, wrapped = ring_slices(tail, n, K)
+            mine = ref_before.clone()
+            for src, dst, cnt in slices:
+                mine[dst:dst + cnt] = items[src:src + cnt]
+            assert torch.equal(mine, q.vector_queue)
+            # the reference leaves tail == K (not 0) when a batch ends exactly at the end of the buffer
+            assert new_tail == q.current_tail
+            tail = new_tail
+    with pytest.raises(ValueError):
+        ring_slices(0, 5, 4)
+
+
+def test_activation_arena_reuses_buffers():
+    from vince_b200.encoder import _Arena
+    a = _Arena("cpu")
+    t1 = a.alloc((1000, 64), torch.float32)
+    a.free(t1)
+    t2 = a.alloc((2000, 64), torch.bfloat16)        # same byte size: must reuse
+    assert t2.data_ptr() == t1.data_ptr() and a.total == 1000 * 64 * 4
+    t3 = a.alloc((10,), torch.float32)
+    assert t3.data_ptr() != t2.data_ptr()
