@@ -40,13 +40,19 @@ def main():
     run = ops.build_conv_fwd(x_hi, x_lo, w_hi, w_lo, out, M, Cout, K, geom=geom, block_n=a.bn, stats=stats, halo_mode=a.halo)
     run()
     torch.cuda.synchronize()
-    trace = torch.zeros((4, 512), device=dev, dtype=torch.int64)
+    trace = torch.zeros((16, 512), device=dev, dtype=torch.int64)
     os.environ["VINCE_B200_TRACE_PTR"] = str(trace.data_ptr())
     run()
     torch.cuda.synchronize()
     del os.environ["VINCE_B200_TRACE_PTR"]
-    t = trace.cpu().numpy()
-    t0 = t[t > 0].min()
+    full = trace.cpu().numpy()
+    t = full[:8]
+    t0 = full[full > 0].min()
+    if (full[8:] > 0).any():
+        print("pair trace (ns since first event): kb | leader: A-slot B-slot data issued | peer: A-slot B-slot data-local")
+        for i in range(24):
+            print("%3d | %7d %7d %7d %7d | %7d %7d %7d" % (i, full[4][i] - t0, full[0][i] - t0, full[1][i] - t0, full[2][i] - t0,
+                                                           full[12][i] - t0, full[8][i] - t0, full[13][i] - t0))
     n = int((t[1] > 0).sum())
     print("%s: %d k-blocks traced for CTA 0 (cycles relative to first event)" % (name, n))
     print("  kb   prod_slot   mma_data  mma_issued   d(data)  d(issued)  issue_len   data-prod")

@@ -21,6 +21,8 @@
 // updates the running statistics, so no separate BN-finalize launch exists).  Accumulators are double-buffered in
 // TMEM so the epilogue of tile t overlaps the main loop of tile t+1.  One CTA per SM; tiles are handed out round-robin
 // with the M index fastest so that concurrently running CTAs share the weight tile through L2.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -29,7 +31,9 @@ namespace vb {
 constexpr int BM = 128;          // rows (output positions) per tile == UMMA M == TMEM lanes
 constexpr int BK = 64;           // bf16 elements per k-block        == one 128-byte swizzle row
 constexpr int UMMA_K = 16;       // bf16
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 288;       // 4 TMA producer warps + 1 MMA warp + 4 epilogue warps
+constexpr int EPI_WARP0 = 5;            // first epilogue warp
+constexpr int EPI_TID0 = EPI_WARP0 * 32;
 constexpr int MAX_RING = 8;
 constexpr int STAGING_BYTES = BM * 128;   // 128 rows x 32 fp32
 
@@ -60,13 +64,18 @@ struct GemmKernelParams {
   unsigned int* bn_counter;
   float bn_momentum, bn_eps;
   double bn_count;
+  int debug_skip_mma;            // debug only: issue no MMAs (pure TMA-pipeline timing), results are garbage
   unsigned long long* trace;     // debug timeline (VB_TRACE builds only): [4 tags][512] clock64 stamps of CTA 0
 };
 
 #ifdef VB_TRACE
 #define VB_TRACE_EVENT(tag, idx)                                                              \
   do {                                                                                        \
-    if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 512) p.trace[(tag) * 512 + (idx)] = clock64(); \
+    if (p.trace != nullptr && blockIdx.x < 2 && (idx) < 512) {                                \
+      unsigned long long _t;                                                                  \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                  \
+      p.trace[(blockIdx.x * 8 + (tag)) * 512 + (idx)] = _t;                                   \
+    }                                                                                         \
   } while (0)
 #else
 #define VB_TRACE_EVENT(tag, idx) \
@@ -89,7 +98,10 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
                : "memory");
 }
 
-template <int BN>
+// CG = 1: one CTA per 128-row tile.  CG = 2: a CTA pair (cluster of 2 on one TPC) computes a 256-row tile with
+// tcgen05.mma.cta_group::2 - the leader's single issuing thread drives both SMs' tensor cores, each CTA loads its own
+// 128 A rows and HALF of the weight tile, which halves both the MMA-dispatch load and the weight bytes per SM.
+template <int BN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B tiles
@@ -98,9 +110,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int planes = (p.passes == 3) ? 2 : 1;
-  constexpr uint32_t B_TILE = BN * 128;
+  constexpr uint32_t B_TILE = (BN / CG) * 128;     // weight rows held by THIS CTA
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int tile_start = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t a_stage_bytes = p.a_plane_bytes * planes;
   const uint32_t b_stage_bytes = B_TILE * planes;
+  const bool merged = (p.b_per_a == 1);            // A and B rings advance in lockstep and share barriers
 
   uint8_t* a_ring = smem;
   uint8_t* b_ring = a_ring + (size_t)p.a_stages * a_stage_bytes;
@@ -123,119 +139,174 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       tma_prefetch_desc(&p.a_lo);
       tma_prefetch_desc(&p.b_lo);
     }
+    // "full" barriers: every CTA's TMA loads signal its OWN barrier (local complete_tx); in a pair the leader's
+    // barrier takes one more arrival, forwarded by the peer's otherwise idle warp 1 once the peer's data has landed
+    // one arrival (with its expect_tx) per producer warp = per bf16 plane.  When every A load pairs with exactly
+    // one B load (tiled / im2col modes) both operands share the B ring's barriers: one wait per k-block.
+    const uint32_t fwd = (CG == 2 && cta_rank == 0) ? 1u : 0u;
     for (int s = 0; s < p.a_stages; ++s) {
-      mbar_init(&a_full[s], 1);
+      mbar_init(&a_full[s], (uint32_t)planes + fwd);
       mbar_init(&a_empty[s], 1);
     }
     for (int s = 0; s < p.b_stages; ++s) {
-      mbar_init(&b_full[s], 1);
+      mbar_init(&b_full[s], (uint32_t)planes * (merged ? 2u : 1u) + fwd);
       mbar_init(&b_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 128);
+      mbar_init(&tmem_empty[s], CG == 2 ? 8 : 128);    // pair: one arrive per epilogue warp of both CTAs
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
-    tmem_alloc(tmem_ptr, 2 * BN);
-    tmem_relinquish();
+  if (warp == 4) {
+    if (CG == 2) {
+      tmem_alloc2(tmem_ptr, 2 * BN);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_ptr, 2 * BN);
+      tmem_relinquish();
+    }
   }
-  if (threadIdx.x >= 64) {
-    for (int i = threadIdx.x - 64; i < 8 * BN; i += 128) smem_stats[i] = 0.0;
+  if (threadIdx.x >= EPI_TID0) {
+    for (int i = threadIdx.x - EPI_TID0; i < 8 * BN; i += 128) smem_stats[i] = 0.0;
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();                 // peer barriers initialised before any remote arrive / multicast
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;   // num_m_blocks counts 128*CG-row tiles
 
   // The producer and MMA warps keep their control flow WARP-UNIFORM (all 32 lanes walk the loops and wait on the
   // barriers) and elect one lane only around the TMA / tcgen05 instructions themselves: tile indices, stage
   // counters, smem addresses and descriptors then live in uniform registers, which is what UTMALDG / UTCHMMA
   // consume.  Running the whole loop under `if (lane == 0)` makes ptxas treat every operand as divergent and
   // emit a waterfall of R2UR moves per instruction (~90 cycles per MMA issue, measured).
-  if (warp == 0) {
-    // ======================= TMA producer =======================
-    int as = 0, bs = 0;
-    uint32_t aphase = 0, bphase = 0;
-    int tr_p = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % p.num_m_blocks;
-      const int n_blk = tile / p.num_m_blocks;
-      const int m0 = m_blk * BM;
-      int img = 0, ph = 0, qw = 0;
-      if (p.a_mode == 1) {
-        img = m0 / p.PQ;
-        const int rem = m0 - img * p.PQ;
-        const int p0 = rem / p.Q;
-        const int q0 = rem - p0 * p.Q;
-        ph = p0 * p.stride - p.pad_h;
-        qw = q0 * p.stride - p.pad_w;
-      } else if (p.a_mode == 2) {
-        img = m_blk / p.tiles_per_img;
-        ph = (m_blk - img * p.tiles_per_img) * p.TH - 1;        // first halo row
-      }
-      for (int ac = 0; ac < p.a_chunks; ++ac) {
-        mbar_wait(&a_empty[as], aphase ^ 1);
-        uint8_t* a_hi = a_ring + (size_t)as * a_stage_bytes;
-        uint8_t* a_lo = a_hi + p.a_plane_bytes;
-        int tap = 0, cb = 0, r = 0, sx = 0;
+  if (warp < 2) {
+    // ======================= TMA producers, activations: warp 0 = hi plane, warp 1 = lo plane =======================
+    // (a single thread can only issue a TMA load every ~250 cycles, measured; one warp per operand plane keeps the
+    //  four loads of a k-block in flight concurrently)
+    const int plane = warp;
+    if (plane < planes) {
+      const CUtensorMap* amap = plane == 0 ? &p.a_hi : &p.a_lo;
+      int as = 0;
+      uint32_t aphase = 0;
+      int tr_a = 0;
+      for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
+        const int m_blk = (tile % p.num_m_blocks) * CG + (int)cta_rank;
+        const int m0 = m_blk * BM;
+        int img = 0, ph = 0, qw = 0;
         if (p.a_mode == 1) {
-          tap = ac / p.cin_blocks;
-          cb = ac - tap * p.cin_blocks;
-          r = tap / p.S;
-          sx = tap - r * p.S;
+          img = m0 / p.PQ;
+          const int rem = m0 - img * p.PQ;
+          const int p0 = rem / p.Q;
+          const int q0 = rem - p0 * p.Q;
+          ph = p0 * p.stride - p.pad_h;
+          qw = q0 * p.stride - p.pad_w;
+        } else if (p.a_mode == 2) {
+          img = m_blk / p.tiles_per_img;
+          ph = (m_blk - img * p.tiles_per_img) * p.TH - 1;        // first halo row
         }
-        if (elect_one()) {
-          mbar_expect_tx(&a_full[as], p.a_tx_bytes * planes);
-          if (p.a_mode == 0) {
-            tma_load_2d(a_hi, &p.a_hi, &a_full[as], ac * BK, m0);
-            if (planes == 2) tma_load_2d(a_lo, &p.a_lo, &a_full[as], ac * BK, m0);
-          } else if (p.a_mode == 1) {
-            tma_load_im2col_4d(a_hi, &p.a_hi, &a_full[as], cb * BK, qw, ph, img, (uint16_t)sx, (uint16_t)r);
-            if (planes == 2)
-              tma_load_im2col_4d(a_lo, &p.a_lo, &a_full[as], cb * BK, qw, ph, img, (uint16_t)sx, (uint16_t)r);
-          } else {
-            tma_load_4d(a_hi, &p.a_hi, &a_full[as], ac * BK, -1, ph, img);
-            if (planes == 2) tma_load_4d(a_lo, &p.a_lo, &a_full[as], ac * BK, -1, ph, img);
+        for (int ac = 0; ac < p.a_chunks; ++ac) {
+          uint64_t* a_full_bar = merged ? &b_full[as] : &a_full[as];
+          mbar_wait(merged ? &b_empty[as] : &a_empty[as], aphase ^ 1);
+          if (lane == 0 && plane == 0) VB_TRACE_EVENT(4, tr_a);
+          ++tr_a;
+          uint8_t* dst = a_ring + (size_t)as * a_stage_bytes + (size_t)plane * p.a_plane_bytes;
+          int tap = 0, cb = 0, r = 0, sx = 0;
+          if (p.a_mode == 1) {
+            tap = ac / p.cin_blocks;
+            cb = ac - tap * p.cin_blocks;
+            r = tap / p.S;
+            sx = tap - r * p.S;
           }
-        }
-        __syncwarp();
-        if (++as == p.a_stages) {
-          as = 0;
-          aphase ^= 1;
-        }
-        for (int bi = 0; bi < p.b_per_a; ++bi) {
-          mbar_wait(&b_empty[bs], bphase ^ 1);
-          if (lane == 0) VB_TRACE_EVENT(0, tr_p);
-          ++tr_p;
-          uint8_t* b_hi = b_ring + (size_t)bs * b_stage_bytes;
-          uint8_t* b_lo = b_hi + B_TILE;
-          // weight k-block: modes 0/1 -> ac; halo -> tap bi, channel block ac
-          const int kb = (p.a_mode == 2) ? (bi * p.a_chunks + ac) : ac;
           if (elect_one()) {
-            mbar_expect_tx(&b_full[bs], b_stage_bytes);
-            tma_load_2d(b_hi, &p.b_hi, &b_full[bs], kb * BK, n_blk * BN);
-            if (planes == 2) tma_load_2d(b_lo, &p.b_lo, &b_full[bs], kb * BK, n_blk * BN);
+            if (p.debug_skip_mma & 2) mbar_arrive(a_full_bar);
+            else {
+            mbar_expect_tx(a_full_bar, p.a_tx_bytes);
+            if (p.a_mode == 0) tma_load_2d(dst, amap, a_full_bar, ac * BK, m0);
+            else if (p.a_mode == 1) tma_load_im2col_4d(dst, amap, a_full_bar, cb * BK, qw, ph, img, (uint16_t)sx, (uint16_t)r);
+            else tma_load_4d(dst, amap, a_full_bar, ac * BK, -1, ph, img);
+            }
           }
           __syncwarp();
-          if (++bs == p.b_stages) {
-            bs = 0;
-            bphase ^= 1;
+          if (++as == p.a_stages) {
+            as = 0;
+            aphase ^= 1;
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    constexpr uint32_t idesc = make_idesc(UMMA_FMT_BF16, BM, BN);
+  } else if (warp < 4) {
+    // ======================= TMA producers, weights: warp 2 = hi plane, warp 3 = lo plane =======================
+    const int plane = warp - 2;
+    if (plane < planes) {
+      const CUtensorMap* bmap = plane == 0 ? &p.b_hi : &p.b_lo;
+      int bs = 0;
+      uint32_t bphase = 0;
+      int tr_p = 0;
+      for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
+        const int n_blk = tile / p.num_m_blocks;
+        // this CTA's share of the weight tile (all of it, or its half when paired)
+        const int nrow = n_blk * BN + (int)cta_rank * (BN / CG);
+        for (int ac = 0; ac < p.a_chunks; ++ac) {
+          for (int bi = 0; bi < p.b_per_a; ++bi) {
+            mbar_wait(&b_empty[bs], bphase ^ 1);
+            if (lane == 0 && plane == 0) VB_TRACE_EVENT(0, tr_p);
+            ++tr_p;
+            uint8_t* dst = b_ring + (size_t)bs * b_stage_bytes + (size_t)plane * B_TILE;
+            // weight k-block: modes 0/1 -> ac; halo -> tap bi, channel block ac
+            const int kb = (p.a_mode == 2) ? (bi * p.a_chunks + ac) : ac;
+            if (elect_one()) {
+              if (p.debug_skip_mma & 4) mbar_arrive(&b_full[bs]);
+              else {
+                mbar_expect_tx(&b_full[bs], B_TILE);
+                tma_load_2d(dst, bmap, &b_full[bs], kb * BK, nrow);
+              }
+            }
+            __syncwarp();
+            if (++bs == p.b_stages) {
+              bs = 0;
+              bphase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ======================= MMA issuer (leader CTA only when CG == 2) =======================
+    constexpr uint32_t idesc = make_idesc(UMMA_FMT_BF16, BM * CG, BN);
     int as = 0, bs = 0;
     uint32_t aphase = 0, bphase = 0;
     int local_t = 0;
     int tr_m = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_t) {
+    if (CG == 2 && cta_rank == 1) {
+      // peer CTA: forward "my operands have landed" to the leader's barriers, one remote arrive per stage use
+      for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
+        for (int ac = 0; ac < p.a_chunks; ++ac) {
+          if (!merged) {
+            mbar_wait(&a_full[as], aphase);
+            if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&a_full[as]), 0));
+          }
+          for (int bi = 0; bi < p.b_per_a; ++bi) {
+            mbar_wait(&b_full[bs], bphase);
+            if (lane == 0) VB_TRACE_EVENT(5, tr_m);
+            ++tr_m;
+            if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&b_full[bs]), 0));
+            if (++bs == p.b_stages) {
+              bs = 0;
+              bphase ^= 1;
+            }
+          }
+          if (++as == p.a_stages) {
+            as = 0;
+            aphase ^= 1;
+          }
+        }
+      }
+    }
+    for (int tile = (cta_rank == 0 ? tile_start : num_tiles); tile < num_tiles; tile += tile_step, ++local_t) {
       const int acc = local_t & 1;
       const uint32_t acc_phase = (local_t >> 1) & 1;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -243,7 +314,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       const uint32_t d_tmem = tmem_base + acc * BN;
       uint32_t accumulate = 0;
       for (int ac = 0; ac < p.a_chunks; ++ac) {
-        mbar_wait(&a_full[as], aphase);
+        if (!merged) mbar_wait(&a_full[as], aphase);
         const uint32_t a_hi0 = smem_u32(a_ring + (size_t)as * a_stage_bytes);
         for (int bi = 0; bi < p.b_per_a; ++bi) {
           mbar_wait(&b_full[bs], bphase);
@@ -259,9 +330,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
           const uint64_t db_lo0 = make_smem_desc(b_hi + B_TILE, 16, 1024, UMMA_LAYOUT_SW128);
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
+            for (int k = 0; k < ((p.debug_skip_mma & 1) ? 0 : BK / UMMA_K); ++k) {
               const uint64_t kadv = (uint64_t)(k * UMMA_K * 2 / 16);
-              if (planes == 2) {
+              if (CG == 2) {
+                if (planes == 2) {
+                  umma2_bf16(d_tmem, da_lo0 + kadv, db_hi0 + kadv, idesc, accumulate);
+                  umma2_bf16(d_tmem, da_hi0 + kadv, db_lo0 + kadv, idesc, 1);
+                  umma2_bf16(d_tmem, da_hi0 + kadv, db_hi0 + kadv, idesc, 1);
+                } else {
+                  umma2_bf16(d_tmem, da_hi0 + kadv, db_hi0 + kadv, idesc, accumulate);
+                }
+              } else if (planes == 2) {
                 // small cross terms first, dominant term last
                 umma_bf16(d_tmem, da_lo0 + kadv, db_hi0 + kadv, idesc, accumulate);
                 umma_bf16(d_tmem, da_hi0 + kadv, db_lo0 + kadv, idesc, 1);
@@ -271,11 +350,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
               }
               accumulate = 1;
             }
-            umma_commit(&b_empty[bs]);             // frees the weight slot when these MMAs retire
-            if (bi == p.b_per_a - 1) umma_commit(&a_empty[as]);   // ... and the activation slot after its last tap
-            if (bi == p.b_per_a - 1 && ac == p.a_chunks - 1) umma_commit(&tmem_full[acc]);   // accumulator ready
+            const bool last_b = (bi == p.b_per_a - 1);
+            if (CG == 2) {
+              umma2_commit_multicast(&b_empty[bs]);                        // frees the weight slot in BOTH CTAs
+              if (last_b && !merged) umma2_commit_multicast(&a_empty[as]); // ... the activation slot after its last tap
+              if (last_b && ac == p.a_chunks - 1) umma2_commit_multicast(&tmem_full[acc]);   // accumulators ready
+            } else {
+              umma_commit(&b_empty[bs]);           // frees the weight slot when these MMAs retire
+              if (last_b && !merged) umma_commit(&a_empty[as]);
+              if (last_b && ac == p.a_chunks - 1) umma_commit(&tmem_full[acc]);
+            }
           }
-          __syncwarp();
           accumulate = 1;
           if (lane == 0) VB_TRACE_EVENT(2, tr_m);
           ++tr_m;
@@ -294,7 +379,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     // ======================= epilogue (warps 2..5) =======================
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
-    const int etid = threadIdx.x - 64;             // 0..127
+    const int etid = threadIdx.x - EPI_TID0;       // 0..127
     const bool store_leader = (etid == 0);
     // halo mode: which output pixel (if any) this accumulator row is
     int hy = 0, hx = 0;
@@ -305,8 +390,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     int local_t = 0;
     int cur_n_blk = -1;
     bool store_pending = false;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_t) {
-      const int m_blk = tile % p.num_m_blocks;
+    uint32_t tmem_empty_leader[2] = {0u, 0u};
+    if (CG == 2) {
+      tmem_empty_leader[0] = mapa_shared(smem_u32(&tmem_empty[0]), 0);
+      tmem_empty_leader[1] = mapa_shared(smem_u32(&tmem_empty[1]), 0);
+    }
+    for (int tile = tile_start; tile < num_tiles; tile += tile_step, ++local_t) {
+      const int m_blk = (tile % p.num_m_blocks) * CG + (int)cta_rank;
       const int n_blk = tile / p.num_m_blocks;
       const int acc = local_t & 1;
       const uint32_t acc_phase = (local_t >> 1) & 1;
@@ -351,7 +441,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         if (chunk == BN / 32 - 1) {
           // all TMEM reads of this accumulator are done: hand it back to the MMA warp
           tc_fence_before_sync();
-          mbar_arrive(&tmem_empty[acc]);
+          if (CG == 2) {
+            // the leader's MMA warp owns both accumulators: one remote arrive per epilogue warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tmem_empty_leader[acc]);
+          } else {
+            mbar_arrive(&tmem_empty[acc]);
+          }
         }
         float v[32];
 #pragma unroll
@@ -462,9 +558,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) {
+  if (CG == 2) cluster_sync_all();                 // no CTA of the pair may exit while the other can still signal it
+  if (warp == 4) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 2 * BN);
+    if (CG == 2) tmem_dealloc2(tmem_base, 2 * BN);
+    else tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -507,10 +605,28 @@ static size_t fixed_smem(int bn) {
   return 1024 /*align slack*/ + STAGING_BYTES + (4 * MAX_RING + 4) * 8 + 16 + 8 * bn * 8;
 }
 
-template <int BN>
+template <int BN, int CG>
 static int launch_gemm(const GemmKernelParams& kp, size_t smem, int grid, cudaStream_t stream) {
-  VB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  conv_gemm_kernel<BN><<<grid, GEMM_THREADS, smem, stream>>>(kp);
+  VB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (CG == 1 && !getenv("VINCE_B200_CLUSTER_ONLY")) {
+    conv_gemm_kernel<BN, CG><<<grid, GEMM_THREADS, smem, stream>>>(kp);
+  } else {
+    grid &= ~1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CG>, kp));
+  }
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }
@@ -518,20 +634,22 @@ static int launch_gemm(const GemmKernelParams& kp, size_t smem, int grid, cudaSt
 // Tile width policy.  Measured on B200 (profiles/r01_conv_timeline.md): a tcgen05.mma dispatch from shared-memory
 // operands costs ~22 cycles + max(48, N/2) cycles and every k-block adds ~270 cycles of barrier / descriptor work in
 // the single issuing thread, so wider tiles amortise better - unless they leave SMs idle in the last wave.
-static int auto_block_n(const ConvGemmDesc& d) {
+static int auto_block_n(const ConvGemmDesc& d, int cg) {
   const int cands[3] = {256, 128, 64};
-  const long m_blocks = (d.M + BM - 1) / BM;
-  const long sms = num_sms();
+  const long m_blocks = ((d.M + BM - 1) / BM + cg - 1) / cg;
+  const long units = num_sms() / cg;                 // CTAs (cg = 1) or CTA pairs (cg = 2) working concurrently
   long best_cost = -1;
   int best = 64;
   for (int bn : cands) {
-    if (d.N % bn != 0 && !(bn == 64 && d.N < 128)) continue;
-    if (bn == 64 && d.N % 64 != 0 && d.N > 64) continue;
+    if (bn > 64 && d.N % bn != 0) continue;
     const long tiles = m_blocks * ((d.N + bn - 1) / bn);
-    const long waves = (tiles + sms - 1) / sms;
-    const long dispatch = 22 + (bn / 2 > 48 ? bn / 2 : 48);
+    const long waves = (tiles + units - 1) / units;
     const long passes = d.passes == 3 ? 3 : 1;
-    const long mainloop = (long)(d.K / BK) * (4 * passes * dispatch + 270);
+    // issue side: per-MMA dispatch + per-k-block barrier/descriptor overhead; tensor side: bn/2 cycles per MMA per SM
+    const long dispatch = cg == 2 ? 30 + bn / 8 : 22 + (bn / 2 > 48 ? bn / 2 : 48);
+    const long issue = 4 * passes * dispatch + (cg == 2 ? 500 : 270);
+    const long pipe = 4 * passes * (bn / 2 > 48 ? bn / 2 : 48);
+    const long mainloop = (long)(d.K / BK) * (issue > pipe ? issue : pipe);
     const long epilogue = 900L * (bn / 32);          // overlaps the next tile's main loop (double-buffered TMEM)
     const long cost = waves * (mainloop > epilogue ? mainloop : epilogue);
     if (best_cost < 0 || cost < best_cost) best_cost = cost, best = bn;
@@ -553,7 +671,7 @@ static int halo_tile_rows(const ConvGemmDesc& d) {
   const double eff = (double)(d.H * d.W) / ((double)tiles_per_img * BM);
   if (d.halo_mode < 0 && eff < 0.7) return 0;
   // two halo stages + at least two weight stages must fit in shared memory, else fall back to im2col
-  int bn = d.block_n ? d.block_n : auto_block_n(d);
+  int bn = d.block_n ? d.block_n : auto_block_n(d, ((d.M + BM - 1) / BM >= 8) ? 2 : 1);
   const size_t planes = d.passes == 3 ? 2 : 1;
   const size_t a_stage = (size_t)(((th + 2) * Wp + 7) / 8) * 1024 * planes;
   const size_t b_stage = (size_t)bn * 128 * planes;
@@ -571,10 +689,16 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   VB_REQUIRE(!(d.stats && (d.bias || d.scale || d.relu)), "conv_gemm: stats are defined on raw accumulators only");
   VB_REQUIRE(!d.bn_coef || (d.stats && d.bn_gamma && d.bn_beta && d.bn_running_mean && d.bn_running_var && d.bn_counter),
              "conv_gemm: BatchNorm finalize needs stats, gamma, beta, running stats and a counter");
-  int bn = d.block_n;
-  if (bn == 0) bn = auto_block_n(d);
-  VB_REQUIRE(bn == 64 || bn == 128 || bn == 256, "conv_gemm: block_n must be 64/128/256");
   const size_t planes = d.passes == 3 ? 2 : 1;
+  // CTA pairs (cta_group::2): worthwhile whenever there are at least a few 256-row tiles per SM pair
+  int cg = ((d.M + BM - 1) / BM >= 8) ? 2 : 1;
+  {
+    const char* e = getenv("VINCE_B200_CTA_PAIR");     // 0 forces single-CTA tiles (debug / A-B comparison)
+    if (e && atoi(e) == 0) cg = 1;
+  }
+  int bn = d.block_n;
+  if (bn == 0) bn = auto_block_n(d, cg);
+  VB_REQUIRE(bn == 64 || bn == 128 || bn == 256, "conv_gemm: block_n must be 64/128/256");
 
   GemmKernelParams kp;
   memset(&kp, 0, sizeof(kp));
@@ -592,6 +716,7 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   kp.bn_coef = d.bn_coef, kp.bn_counter = d.bn_counter, kp.bn_momentum = d.bn_momentum, kp.bn_eps = d.bn_eps;
   kp.bn_count = (double)d.M;
   kp.trace = reinterpret_cast<unsigned long long*>(d.trace);
+  kp.debug_skip_mma = getenv("VINCE_B200_DEBUG_SKIP_MMA") ? atoi(getenv("VINCE_B200_DEBUG_SKIP_MMA")) : 0;
   kp.a_plane_bytes = BM * 128;
   kp.a_tx_bytes = BM * 128;
   kp.a_chunks = d.K / BK;
@@ -660,11 +785,12 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
       if (rc) return rc;
     }
   }
-  rc = encode_tma_2d(&kp.b_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d.b_hi, d.K, d.N, (uint64_t)d.K * 2, BK, bn,
+  // each CTA of a pair loads its half of the weight tile
+  rc = encode_tma_2d(&kp.b_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d.b_hi, d.K, d.N, (uint64_t)d.K * 2, BK, bn / cg,
                      CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   if (d.passes == 3) {
-    rc = encode_tma_2d(&kp.b_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d.b_lo, d.K, d.N, (uint64_t)d.K * 2, BK, bn,
+    rc = encode_tma_2d(&kp.b_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d.b_lo, d.K, d.N, (uint64_t)d.K * 2, BK, bn / cg,
                        CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
@@ -676,7 +802,7 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
 
   // ---- shared-memory budget: A ring + B ring ----
   const size_t a_stage = (size_t)kp.a_plane_bytes * planes;
-  const size_t b_stage = (size_t)bn * 128 * planes;
+  const size_t b_stage = (size_t)(bn / cg) * 128 * planes;
   const size_t avail = SMEM_BUDGET - fixed_smem(bn);
   if (kp.a_mode == 2) {
     kp.a_stages = 2;
@@ -690,11 +816,20 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
     kp.a_stages = kp.b_stages = st;
   }
   const size_t smem = fixed_smem(bn) + kp.a_stages * a_stage + kp.b_stages * b_stage;
+  // 128-row blocks -> (128*cg)-row tiles; a pair whose second half lies past the end loads zeros and stores nothing
+  kp.num_m_blocks = (kp.num_m_blocks + cg - 1) / cg;
   const int tiles = kp.num_m_blocks * kp.num_n_blocks;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  if (bn == 64) return launch_gemm<64>(kp, smem, grid, stream);
-  if (bn == 128) return launch_gemm<128>(kp, smem, grid, stream);
-  return launch_gemm<256>(kp, smem, grid, stream);
+  int grid = tiles * cg < num_sms() ? tiles * cg : num_sms();
+  if (getenv("VINCE_B200_DEBUG_GRID") && atoi(getenv("VINCE_B200_DEBUG_GRID")) < grid) grid = atoi(getenv("VINCE_B200_DEBUG_GRID"));
+  if (cg == 2) {
+    grid &= ~1;
+    if (bn == 64) return launch_gemm<64, 2>(kp, smem, grid, stream);
+    if (bn == 128) return launch_gemm<128, 2>(kp, smem, grid, stream);
+    return launch_gemm<256, 2>(kp, smem, grid, stream);
+  }
+  if (bn == 64) return launch_gemm<64, 1>(kp, smem, grid, stream);
+  if (bn == 128) return launch_gemm<128, 1>(kp, smem, grid, stream);
+  return launch_gemm<256, 1>(kp, smem, grid, stream);
 }
 
 }  // namespace vb
