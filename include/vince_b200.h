@@ -11,10 +11,10 @@
  *   - all tensor arguments are raw DEVICE pointers owned by the caller, with explicit shapes; nothing is
  *     allocated inside (scratch comes in through `workspace` arguments sized by *_workspace_bytes());
  *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
- *   - activations between convolutions are NHWC, carried as a pair of bf16 planes (hi, lo) with
+ *   - activations between convolutions are NHWC, carried as a pair of fp16 planes (hi, lo) with
  *     x ~= hi + lo (|err| <= 2^-17 |x|); with `passes` = 3 each MMA k-step computes hi*hi + lo*hi + hi*lo so
  *     the result matches the reference's fp32 arithmetic to ~1e-5; `passes` = 1 uses the hi plane only
- *     (plain bf16, lo pointers may be NULL).
+ *     (plain fp16, lo pointers may be NULL).
  */
 #ifndef VINCE_B200_H_
 #define VINCE_B200_H_
@@ -49,9 +49,9 @@ int vince_abi_version(void);
  * 3x3 stride-1 pad-1 convolutions use a shared-memory halo path (one TMA load per tile serves all nine taps) when
  * halo_mode = -1 (auto) finds it efficient, or always when halo_mode = 1; 0 forces the TMA-im2col path. */
 typedef struct {
-  const void* a_hi;       /* bf16: [M,K] row-major, or NHWC [batch,H,W,Cin] when im2col != 0 */
+  const void* a_hi;       /* fp16: [M,K] row-major, or NHWC [batch,H,W,Cin] when im2col != 0 */
   const void* a_lo;
-  const void* w_hi;       /* bf16 [N,K], K ordered (r, s, cin): see vince_weight_prep */
+  const void* w_hi;       /* fp16 [N,K], K ordered (r, s, cin): see vince_weight_prep */
   const void* w_lo;
   float* out;
   int32_t M, N, K;
@@ -72,28 +72,39 @@ typedef struct {
   float* bn_coef;
   uint32_t* bn_counter;   /* one zero-initialised word per launch */
   float bn_momentum, bn_eps;
+  /* im2col only: element strides of the activation tensor between pixels / rows / images; 0 = dense NHWC
+   * (Cin, W*Cin, H*W*Cin).  A pixel stride smaller than Cin describes overlapping pixel windows (the packed
+   * stem input of vince_stem_pack). */
+  int64_t a_pixel_stride, a_row_stride, a_img_stride;
+  float alpha;            /* accumulators are multiplied by alpha before the epilogue (0 = 1): undoes the exact
+                           * power-of-two pre-scale of vince_weight_prep */
+  int32_t reserved;
 } vince_conv_desc;
 int vince_conv_fwd(const vince_conv_desc* desc, void* stream);
 /* eval-mode BatchNorm coefficients from the running statistics: coef[2][C] */
 int vince_bn_eval_coef(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                        float eps, float* coef, int32_t C, void* stream);
 
-/* ---- stem input packing: NCHW fp32 -> X[n, j, q, 64] bf16 (hi, lo) ------------------------------------------
+/* ---- stem input packing: NCHW fp32 -> X[n, a, b, 16] fp16 (hi, lo), overlapping-window layout ---------------
  * replaces: the input side of conv1 (7x7/2, pad 3; resnet.py:170,233) and the shuffle gather data[shuffle_order]
  *           (vince_model.py:142) when gather_idx != NULL.
- * X[n,j,q, r2*21+s*3+c] = x[gather_idx[n], c, 2j-1+r2, 2q-3+s]; Hj = H/2+1, Q = (W-1)/2+1.  The stem then runs as
- * vince_conv_fwd with batch,H,W,Cin = N,Hj,Q,64, R=4,S=1, stride 1, pad_lo_h=1, pad_hi_h = P+2-Hj. */
+ * X[n,a,b,(dr*2+dc)*3+c] = x[gather_idx[n], c, 2(a-2)+dr, 2(b-2)+dc] (0 outside the image and for elements 12..15);
+ * Ha = P+3, Wb = Q+3 with P = (H-1)/2+1, Q = (W-1)/2+1.  The 64 elements starting at (a, b=q) are the 2x8x3 input
+ * window of output column q in row pair a, so the stem runs as vince_conv_fwd with batch,H,W,Cin = N,Ha,Q,64,
+ * R=4, S=1, stride 1, no padding, a_pixel_stride = 16, a_row_stride = 16*Wb, a_img_stride = 16*Wb*Ha and weights
+ * prepared with kind = 1. */
 int vince_stem_pack(const float* x, const int64_t* gather_idx, void* x_hi, void* x_lo, int32_t N, int32_t H, int32_t W,
                     void* stream);
 
-/* ---- weight preparation (multi-tensor): OIHW fp32 -> K-major bf16 (hi, lo) ----------------------------------
+/* ---- weight preparation (multi-tensor): OIHW fp32 -> K-major fp16 (hi, lo) ----------------------------------
  * replaces: nothing in the reference (cuDNN consumes OIHW directly); run after every weight update. */
 typedef struct {
   const float* src;       /* [Cout,Cin,R,S] fp32 */
   int64_t dst_off;        /* element offset into w_hi / w_lo */
   int32_t Cout, Cin, R, S;
-  int32_t kind;           /* 0: [Cout][R][S][Cin];  1: packed 7x7 stem -> [64][4][64] */
-  int32_t pad;
+  int32_t kind;           /* 0: [Cout][R][S][Cin];  1: packed 7x7 stem -> [64][4 row pairs][4 col pairs][16] */
+  int32_t scale_log2;     /* weights are multiplied by 2^scale_log2 before the split, so that the lo plane of O(1e-2)
+                           * weights stays a normal fp16 number; pass alpha = 2^-scale_log2 to vince_conv_fwd */
 } vince_weight_entry;
 int vince_weight_prep(const vince_weight_entry* table_dev, int32_t n_entries, int64_t max_elems, void* w_hi, void* w_lo,
                       void* stream);
@@ -121,7 +132,7 @@ int vince_bn_final_pool(const vince_bn_side* main, int32_t res_kind, const void*
 /* ---- small helpers --------------------------------------------------------------------------------------------
  * vince_l2_normalize replaces F.normalize(dim=1) (vince_model.py:180); the jigsaw pair replaces
  * vince_model.py:144-155 and :164-170. */
-int vince_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream);
+int vince_split_f16(const float* x, void* hi, void* lo, int64_t n, void* stream);
 int vince_round_tf32(const float* x, float* out, int64_t n, void* stream);
 int vince_l2_normalize(const float* x, float* out, int32_t rows, int32_t D, float eps, void* stream);
 int vince_jigsaw_patchify(const float* x, const int64_t* gather_idx, float* out, int32_t N, int32_t C, int32_t H,

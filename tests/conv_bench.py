@@ -3,7 +3,7 @@
     python tests/conv_bench.py [--batch 256] [--filter layer1] [--halo -1|0|1] [--bn 0|64|128|256] [--iters 5]
 
 Prints per-shape time (CUDA events, L2 flushed between iterations by cycling through distinct buffers) and the
-algorithmic TFLOP/s (2*M*N*K, no credit for the three bf16 passes).  Not collected by pytest.
+algorithmic TFLOP/s (2*M*N*K, no credit for the three fp16 passes).  Not collected by pytest.
 """
 import argparse
 import os
@@ -52,10 +52,10 @@ def main():
         M = B * P * Q
         K = R * R * Cin
         nbuf = 3
-        acts = [(torch.randn((B, H, W, Cin), device=dev).to(torch.bfloat16), torch.randn((B, H, W, Cin), device=dev).to(torch.bfloat16) * 0.01)
+        acts = [(torch.randn((B, H, W, Cin), device=dev).to(torch.float16), torch.randn((B, H, W, Cin), device=dev).to(torch.float16) * 0.01)
                 for _ in range(nbuf)]
-        w_hi = (torch.randn((Cout, K), device=dev) * 0.05).to(torch.bfloat16)
-        w_lo = (torch.randn((Cout, K), device=dev) * 0.0005).to(torch.bfloat16)
+        w_hi = (torch.randn((Cout, K), device=dev) * 0.05).to(torch.float16)
+        w_lo = (torch.randn((Cout, K), device=dev) * 0.0005).to(torch.float16)
         outs = [torch.empty((M, Cout), device=dev) for _ in range(nbuf)]
         stats = torch.zeros((2 * Cout,), device=dev, dtype=torch.float64)
         geom = None

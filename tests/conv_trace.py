@@ -26,10 +26,10 @@ def main():
     P = (H + 2 * pad - R) // stride + 1
     Q = (W + 2 * pad - R) // stride + 1
     M, K = B * P * Q, R * R * Cin
-    hi = torch.randn((B, H, W, Cin), device=dev).to(torch.bfloat16)
-    lo = (torch.randn((B, H, W, Cin), device=dev) * 0.01).to(torch.bfloat16)
-    w_hi = (torch.randn((Cout, K), device=dev) * 0.05).to(torch.bfloat16)
-    w_lo = (torch.randn((Cout, K), device=dev) * 0.0005).to(torch.bfloat16)
+    hi = torch.randn((B, H, W, Cin), device=dev).to(torch.float16)
+    lo = (torch.randn((B, H, W, Cin), device=dev) * 0.01).to(torch.float16)
+    w_hi = (torch.randn((Cout, K), device=dev) * 0.05).to(torch.float16)
+    w_lo = (torch.randn((Cout, K), device=dev) * 0.0005).to(torch.float16)
     out = torch.empty((M, Cout), device=dev)
     stats = torch.zeros((2 * Cout,), device=dev, dtype=torch.float64)
     geom = None

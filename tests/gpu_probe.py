@@ -21,8 +21,8 @@ RESULTS = []
 
 
 def split(x):
-    hi = x.to(torch.bfloat16)
-    lo = (x - hi.float()).to(torch.bfloat16)
+    hi = x.to(torch.float16)
+    lo = (x - hi.float()).to(torch.float16)
     return hi.contiguous(), lo.contiguous()
 
 
@@ -40,7 +40,7 @@ def report(name, err, tol, extra=""):
 def weight_table(entries):
     """entries: list of (src_tensor, dst_off, Cout, Cin, R, S, kind) -> uint8 device tensor."""
     dt = np.dtype([("src", "<u8"), ("dst_off", "<i8"), ("Cout", "<i4"), ("Cin", "<i4"), ("R", "<i4"), ("S", "<i4"),
-                   ("kind", "<i4"), ("pad", "<i4")])
+                   ("kind", "<i4"), ("scale_log2", "<i4")])
     arr = np.zeros(len(entries), dtype=dt)
     for i, (src, off, co, ci, r, s, kind) in enumerate(entries):
         arr[i] = (src.data_ptr(), off, co, ci, r, s, kind, 0)
@@ -50,7 +50,7 @@ def weight_table(entries):
 def prep_weight(w, kind=0):
     Cout, Cin, R, S = w.shape
     K = 256 if kind == 1 else R * S * Cin
-    hi = torch.empty((Cout, K), device=DEV, dtype=torch.bfloat16)
+    hi = torch.empty((Cout, K), device=DEV, dtype=torch.float16)
     lo = torch.empty_like(hi)
     tab = weight_table([(w, 0, Cout, Cin, R, S, kind)])
     ops.weight_prep(tab, 1, Cout * K, hi, lo)
@@ -137,7 +137,7 @@ def check_conv_im2col():
     conv_case("conv3x3 s1 7x7 512->512", 4, 7, 7, 512, 512, 3, 1, 1)
     conv_case("conv3x3 s2 15x15 128->256 (odd)", 3, 15, 15, 128, 256, 3, 2, 1)
     conv_case("conv1x1 s1 as im2col 9x9 128->64", 2, 9, 9, 128, 64, 1, 1, 0)
-    conv_case("conv3x3 s1 bf16x1", 2, 14, 14, 64, 64, 3, 1, 1, passes=1)
+    conv_case("conv3x3 s1 fp16x1", 2, 14, 14, 64, 64, 3, 1, 1, passes=1)
     conv_case("conv3x3 s1 14x14 256->256 bn256", 4, 14, 14, 256, 256, 3, 1, 1, bn=256)
 
 
@@ -149,7 +149,7 @@ def check_conv_halo():
     conv_case("halo 15x13 64->128 (odd)", 3, 15, 13, 64, 128, 3, 1, 1, halo=1)
     conv_case("halo 19x19 128->64 b2", 2, 19, 19, 128, 64, 3, 1, 1, halo=1)
     conv_case("halo 8x126 64->64 b2 (Wp=128)", 2, 8, 126, 64, 64, 3, 1, 1, halo=1)
-    conv_case("halo 56x56 bf16x1", 2, 56, 56, 64, 64, 3, 1, 1, passes=1, halo=1)
+    conv_case("halo 56x56 fp16x1", 2, 56, 56, 64, 64, 3, 1, 1, passes=1, halo=1)
     conv_case("halo auto 56x56 64->64 b16", 16, 56, 56, 64, 64, 3, 1, 1, halo=-1)
 
 
@@ -160,8 +160,8 @@ def check_stem():
         w = (torch.randn((64, 3, 7, 7), generator=g) * 0.1).to(DEV)
         perm = torch.randperm(N, generator=g).to(DEV)
         sg = ops.stem_geometry(H, W)
-        P, Q, Hj = sg["P"], sg["Q"], sg["Hj"]
-        x_hi = torch.empty((N, Hj, Q, 64), device=DEV, dtype=torch.bfloat16)
+        P, Q = sg["P"], sg["Q"]
+        x_hi = torch.empty((N, sg["Ha"], sg["Wb"], 16), device=DEV, dtype=torch.float16)
         x_lo = torch.empty_like(x_hi)
         ops.stem_pack(x, perm, x_hi, x_lo)
         w_hi, w_lo = prep_weight(w, kind=1)
@@ -227,7 +227,7 @@ def check_bn_apply():
             for res_kind in (0, 1, 2):
                 bn, bn2 = _BN(C, g), _BN(C, g)
                 coef, coef2 = make_coef(raw, bn, train), make_coef(raw2, bn2, train)
-                out_hi = torch.empty((M, C), device=DEV, dtype=torch.bfloat16)
+                out_hi = torch.empty((M, C), device=DEV, dtype=torch.float16)
                 out_lo = torch.empty_like(out_hi)
                 out_f = torch.empty((M, C), device=DEV)
                 kw = {}
@@ -264,7 +264,7 @@ def check_maxpool_finalpool():
     bn = _BN(C, g)
     flat = raw.reshape(-1, C)
     P2, Q2 = (P - 1) // 2 + 1, (Q - 1) // 2 + 1
-    out_hi = torch.empty((N, P2, Q2, C), device=DEV, dtype=torch.bfloat16)
+    out_hi = torch.empty((N, P2, Q2, C), device=DEV, dtype=torch.float16)
     out_lo = torch.empty_like(out_hi)
     ops.bn_relu_maxpool(ops.bn_side(raw, make_coef(flat, bn, True)), out_hi, out_lo, N, P, Q, C)
     torch.cuda.synchronize()
@@ -275,7 +275,7 @@ def check_maxpool_finalpool():
     N, P, Q, C = 2, 112, 112, 64
     raw = torch.randn((N, P, Q, C), generator=g).to(DEV)
     flat = raw.reshape(-1, C)
-    out_hi = torch.empty((N, 56, 56, C), device=DEV, dtype=torch.bfloat16)
+    out_hi = torch.empty((N, 56, 56, C), device=DEV, dtype=torch.float16)
     out_lo = torch.empty_like(out_hi)
     ops.bn_relu_maxpool(ops.bn_side(raw, make_coef(flat, bn, True)), out_hi, out_lo, N, P, Q, C)
     torch.cuda.synchronize()
@@ -309,10 +309,10 @@ def check_small():
     out = torch.empty_like(x)
     ops.l2_normalize(x, out)
     report("l2_normalize", rel(out, F.normalize(x.double(), dim=1)), 1e-6)
-    hi = torch.empty(x.shape, device=DEV, dtype=torch.bfloat16)
+    hi = torch.empty(x.shape, device=DEV, dtype=torch.float16)
     lo = torch.empty_like(hi)
-    ops.split_bf16(x, hi, lo)
-    report("split_bf16", rel(hi.double() + lo.double(), x), 2e-5)
+    ops.split_f16(x, hi, lo)
+    report("split_f16", rel(hi.double() + lo.double(), x), 2e-5)
     r = torch.empty_like(x)
     ops.round_tf32(x, r)
     report("round_tf32", rel(r, x), 3e-4, "low bits zero: %s" % bool(((r.view(torch.int32) & 0x1FFF) == 0).all()))

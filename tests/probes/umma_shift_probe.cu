@@ -56,12 +56,12 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ P
     for (int si = 0; si < p.n_shifts; ++si) {
       const int s = p.shifts[si];
       if (threadIdx.x == 0) {
-        constexpr uint32_t idesc = make_idesc(UMMA_FMT_BF16, 128, N);
+        constexpr uint32_t idesc = make_idesc(UMMA_FMT_F16, 128, N);
         for (int k = 0; k < K / 16; ++k) {
           uint64_t da = make_smem_desc(smem_u32(a_s) + s * 128 + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
           if (variant == 1) da |= (uint64_t)(s & 7) << 49;          // base_offset
           const uint64_t db = make_smem_desc(smem_u32(b_s) + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-          umma_bf16(tmem, da, db, idesc, k != 0);
+          umma_f16(tmem, da, db, idesc, k != 0);
         }
         umma_commit(mma_bar);
       }
@@ -84,12 +84,12 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ P
 }
 
 int main() {
-  std::vector<__nv_bfloat16> a(ROWS * K), b(N * K);
+  std::vector<__half> a(ROWS * K), b(N * K);
   std::vector<float> af(ROWS * K), bf(N * K);
   srand(1);
-  for (int i = 0; i < ROWS * K; ++i) { af[i] = (float)(rand() % 17 - 8); a[i] = __float2bfloat16(af[i]); }
-  for (int i = 0; i < N * K; ++i) { bf[i] = (float)(rand() % 9 - 4); b[i] = __float2bfloat16(bf[i]); }
-  __nv_bfloat16 *da, *db;
+  for (int i = 0; i < ROWS * K; ++i) { af[i] = (float)(rand() % 17 - 8); a[i] = __float2half(af[i]); }
+  for (int i = 0; i < N * K; ++i) { bf[i] = (float)(rand() % 9 - 4); b[i] = __float2half(bf[i]); }
+  __half *da, *db;
   cudaMalloc(&da, a.size() * 2);
   cudaMalloc(&db, b.size() * 2);
   cudaMemcpy(da, a.data(), a.size() * 2, cudaMemcpyHostToDevice);
@@ -101,8 +101,8 @@ int main() {
   const size_t out_elems = (size_t)2 * p.n_shifts * 128 * N;
   cudaMalloc(&p.out, out_elems * 4);
   cudaMemset(p.out, 0xff, out_elems * 4);
-  if (encode_tma_2d(&p.a_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, da, K, ROWS, K * 2, 64, ROWS, CU_TENSOR_MAP_SWIZZLE_128B) ||
-      encode_tma_2d(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, db, K, N, K * 2, 64, N, CU_TENSOR_MAP_SWIZZLE_128B)) {
+  if (encode_tma_2d(&p.a_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, da, K, ROWS, K * 2, 64, ROWS, CU_TENSOR_MAP_SWIZZLE_128B) ||
+      encode_tma_2d(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, db, K, N, K * 2, 64, N, CU_TENSOR_MAP_SWIZZLE_128B)) {
     printf("tma encode failed: %s\n", get_error());
     return 1;
   }

@@ -113,9 +113,12 @@ def test_stem_geometry_and_ring_slices():
     for H in (224, 225, 75, 64, 51):
         sg = ops.stem_geometry(H, H)
         P = (H + 6 - 7) // 2 + 1
-        assert sg["P"] == P and sg["Hj"] == H // 2 + 1
+        assert sg["P"] == P and sg["Ha"] == P + 3 and sg["Wb"] == sg["Q"] + 3
         g = sg["geom"]
         assert (g["H"] + g["pad_lo_h"] + g["pad_hi_h"] - g["R"]) // g["stride"] + 1 == P and g["pad_hi_h"] >= 0
+        # overlapping-window layout: the last 64-element pixel of a row ends exactly at the row's last stored element
+        assert (g["W"] - 1) * g["a_pixel_stride"] + g["Cin"] == g["a_row_stride"]
+        assert g["a_img_stride"] == g["a_row_stride"] * g["H"]
     rng = np.random.RandomState(0)
     for _ in range(200):
         K = int(rng.randint(1, 40))
@@ -143,7 +146,7 @@ def test_activation_arena_reuses_buffers():
     a = _Arena("cpu")
     t1 = a.alloc((1000, 64), torch.float32)
     a.free(t1)
-    t2 = a.alloc((2000, 64), torch.bfloat16)        # same byte size: must reuse
+    t2 = a.alloc((2000, 64), torch.float16)        # same byte size: must reuse
     assert t2.data_ptr() == t1.data_ptr() and a.total == 1000 * 64 * 4
     t3 = a.alloc((10,), torch.float32)
     assert t3.data_ptr() != t2.data_ptr()

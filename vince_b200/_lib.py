@@ -22,6 +22,8 @@ class ConvDesc(Structure):
         ("bn_gamma", c_void_p), ("bn_beta", c_void_p), ("bn_running_mean", c_void_p), ("bn_running_var", c_void_p),
         ("bn_num_batches_tracked", c_void_p), ("bn_coef", c_void_p), ("bn_counter", c_void_p),
         ("bn_momentum", c_float), ("bn_eps", c_float),
+        ("a_pixel_stride", c_int64), ("a_row_stride", c_int64), ("a_img_stride", c_int64),
+        ("alpha", c_float), ("reserved", c_int32),
     ]
 
 
@@ -53,7 +55,7 @@ SIGNATURES = {
                                         c_void_p]),
     "vince_bn_final_pool": (c_int32, [POINTER(BnSide), c_int32, c_void_p, c_void_p, POINTER(BnSide), c_void_p,
                                       c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
-    "vince_split_bf16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "vince_split_f16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "vince_round_tf32": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
     "vince_l2_normalize": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),
     "vince_jigsaw_patchify": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),

@@ -11,8 +11,8 @@
 using namespace vb;
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
-static inline __nv_bfloat16* BF(void* p) { return reinterpret_cast<__nv_bfloat16*>(p); }
-static inline const __nv_bfloat16* BF(const void* p) { return reinterpret_cast<const __nv_bfloat16*>(p); }
+static inline __half* HF(void* p) { return reinterpret_cast<__half*>(p); }
+static inline const __half* HF(const void* p) { return reinterpret_cast<const __half*>(p); }
 
 static BnSide to_side(const vince_bn_side* s) {
   BnSide o;
@@ -46,6 +46,8 @@ int vince_conv_fwd(const vince_conv_desc* d, void* stream) {
   g.bn_gamma = d->bn_gamma, g.bn_beta = d->bn_beta, g.bn_running_mean = d->bn_running_mean;
   g.bn_running_var = d->bn_running_var, g.bn_num_batches_tracked = d->bn_num_batches_tracked;
   g.bn_coef = d->bn_coef, g.bn_counter = d->bn_counter, g.bn_momentum = d->bn_momentum, g.bn_eps = d->bn_eps;
+  g.a_pixel_stride = d->a_pixel_stride, g.a_row_stride = d->a_row_stride, g.a_img_stride = d->a_img_stride;
+  g.alpha = d->alpha;
   g.trace = getenv("VINCE_B200_TRACE_PTR") ? reinterpret_cast<void*>(strtoull(getenv("VINCE_B200_TRACE_PTR"), nullptr, 0)) : nullptr;
   return conv_gemm_launch(g, S(stream));
 }
@@ -60,15 +62,15 @@ int vince_stem_pack(const float* x, const int64_t* gather_idx, void* x_hi, void*
                     void* stream) {
   VB_REQUIRE(x && x_hi, "vince_stem_pack: null pointer");
   VB_REQUIRE(N >= 0 && H > 0 && W > 0, "vince_stem_pack: bad shape N=%d H=%d W=%d", N, H, W);
-  return stem_pack_launch(x, gather_idx, BF(x_hi), BF(x_lo), N, H, W, H / 2 + 1, (W - 1) / 2 + 1, S(stream));
+  return stem_pack_launch(x, gather_idx, HF(x_hi), HF(x_lo), N, H, W, (H - 1) / 2 + 4, (W - 1) / 2 + 4, S(stream));
 }
 
 int vince_weight_prep(const vince_weight_entry* table_dev, int32_t n_entries, int64_t max_elems, void* w_hi, void* w_lo,
                       void* stream) {
   static_assert(sizeof(vince_weight_entry) == sizeof(WeightPrepEntry), "ABI struct mismatch");
   VB_REQUIRE(n_entries == 0 || (table_dev && w_hi), "vince_weight_prep: null pointer");
-  return weight_prep_launch(reinterpret_cast<const WeightPrepEntry*>(table_dev), n_entries, max_elems, BF(w_hi),
-                            BF(w_lo), S(stream));
+  return weight_prep_launch(reinterpret_cast<const WeightPrepEntry*>(table_dev), n_entries, max_elems, HF(w_hi),
+                            HF(w_lo), S(stream));
 }
 
 int vince_bn_apply(const vince_bn_side* main, int32_t res_kind, const void* res_hi, const void* res_lo,
@@ -80,7 +82,7 @@ int vince_bn_apply(const vince_bn_side* main, int32_t res_kind, const void* res_
   VB_REQUIRE(res_kind != 1 || res_hi, "vince_bn_apply: residual planes null");
   if (res_kind == 2 && (rc = check_side(res_bn, "vince_bn_apply(residual)"))) return rc;
   VB_REQUIRE(out_hi || out_f32, "vince_bn_apply: no output");
-  return bn_apply_launch(to_side(main), res_kind, BF(res_hi), BF(res_lo), to_side(res_bn), relu, BF(out_hi), BF(out_lo),
+  return bn_apply_launch(to_side(main), res_kind, HF(res_hi), HF(res_lo), to_side(res_bn), relu, HF(out_hi), HF(out_lo),
                          out_f32, M, C, S(stream));
 }
 
@@ -90,7 +92,7 @@ int vince_bn_relu_maxpool(const vince_bn_side* bn, void* out_hi, void* out_lo, i
   if (rc) return rc;
   VB_REQUIRE(out_hi, "vince_bn_relu_maxpool: null output");
   const int P2 = (P + 2 - 3) / 2 + 1, Q2 = (Q + 2 - 3) / 2 + 1;
-  return bn_relu_maxpool_launch(to_side(bn), BF(out_hi), BF(out_lo), N, P, Q, C, P2, Q2, S(stream));
+  return bn_relu_maxpool_launch(to_side(bn), HF(out_hi), HF(out_lo), N, P, Q, C, P2, Q2, S(stream));
 }
 
 int vince_bn_final_pool(const vince_bn_side* main, int32_t res_kind, const void* res_hi, const void* res_lo,
@@ -102,13 +104,13 @@ int vince_bn_final_pool(const vince_bn_side* main, int32_t res_kind, const void*
   VB_REQUIRE(res_kind != 1 || res_hi, "vince_bn_final_pool: residual planes null");
   if (res_kind == 2 && (rc = check_side(res_bn, "vince_bn_final_pool(residual)"))) return rc;
   VB_REQUIRE(pooled, "vince_bn_final_pool: pooled output null");
-  return bn_final_pool_launch(to_side(main), res_kind, BF(res_hi), BF(res_lo), to_side(res_bn), scatter_idx,
+  return bn_final_pool_launch(to_side(main), res_kind, HF(res_hi), HF(res_lo), to_side(res_bn), scatter_idx,
                               spatial_nchw, pooled, N, HW, C, S(stream));
 }
 
-int vince_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
-  VB_REQUIRE(n == 0 || (x && hi), "vince_split_bf16: null pointer");
-  return split_bf16_launch(x, BF(hi), BF(lo), n, S(stream));
+int vince_split_f16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
+  VB_REQUIRE(n == 0 || (x && hi), "vince_split_f16: null pointer");
+  return split_f16_launch(x, HF(hi), HF(lo), n, S(stream));
 }
 int vince_round_tf32(const float* x, float* out, int64_t n, void* stream) {
   VB_REQUIRE(n == 0 || (x && out), "vince_round_tf32: null pointer");

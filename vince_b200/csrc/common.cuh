@@ -2,7 +2,7 @@
 // UMMA descriptor builders, error plumbing.  Hand-written inline PTX; no CUTLASS/CuTe dependency.
 #pragma once
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -46,7 +46,8 @@ int encode_tma_2d(CUtensorMap* map, CUtensorMapDataType dtype, const void* base,
                   uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz);
 int encode_tma_im2col_nhwc(CUtensorMap* map, CUtensorMapDataType dtype, const void* base, int N, int H, int W, int C,
                            int pad_lo_h, int pad_lo_w, int pad_hi_h, int pad_hi_w, int R, int S, int stride,
-                           uint32_t channels_per_pixel, uint32_t pixels_per_column, CUtensorMapSwizzle swz);
+                           uint32_t channels_per_pixel, uint32_t pixels_per_column, CUtensorMapSwizzle swz,
+                           long long pixel_stride = 0, long long row_stride = 0, long long img_stride = 0);
 
 // NHWC tensor [N,H,W,C] as a 4-D tiled map with box {box_c, box_w, box_h, 1} (halo loads / NHWC tile stores)
 int encode_tma_4d_nhwc(CUtensorMap* map, CUtensorMapDataType dtype, const void* base, int N, int H, int W, int C,
@@ -104,6 +105,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// same, on a shared-memory address (keeps barrier indexing in 32-bit uniform arithmetic)
+__device__ __forceinline__ uint32_t mbar_try_wait_addr(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok;
+}
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait_addr(bar_addr, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("vince_b200: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar_addr, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
+  if (mbar_try_wait_addr(bar_addr, parity)) return;
+  if (mbar_try_wait_addr(bar_addr, parity)) return;
+  mbar_wait_slow(bar_addr, parity);
+}
+
 // ---- proxies / fences ----
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -155,7 +184,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 
 // ---- UMMA (tcgen05.mma), single-CTA, A and B from shared memory ----
 // D[tmem] (+)= A[smem] * B[smem]^T ; `accumulate`==0 overwrites D.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -240,7 +269,7 @@ __device__ __forceinline__ void tmem_relinquish2() {
 __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                            uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -255,6 +284,44 @@ __device__ __forceinline__ void umma2_commit_multicast(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask)
                : "memory");
+}
+
+// tcgen05.mma with the shared-memory descriptors given as 32-bit words: low word per operand (address >> 4 | LBO),
+// one common high word (SBO | version | swizzle mode).  CG = 1: single CTA; CG = 2: CTA pair (issued by the leader).
+template <int CG>
+__device__ __forceinline__ void umma_f16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+  if (CG == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi)
+        : "memory");
+  }
+}
+// commit on a barrier given by its shared-memory address (CG = 2: same offset in both CTAs of the pair)
+template <int CG>
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar_addr) {
+  if (CG == 2) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar_addr), "h"(mask)
+                 : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+  }
 }
 
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (thread t <- lane base+t)
@@ -291,15 +358,24 @@ constexpr uint32_t UMMA_LAYOUT_SW128 = 2;
 
 // Instruction descriptor (kind::f16 / kind::tf32), fp32 accumulate, A and B K-major.
 // c_format=F32 bit[4,6)=1 | a_format [7,10) | b_format [10,13) | N>>3 [17,23) | M>>4 [24,29)
-constexpr uint32_t UMMA_FMT_BF16 = 1, UMMA_FMT_TF32 = 2;
+constexpr uint32_t UMMA_FMT_F16 = 0, UMMA_FMT_TF32 = 2;
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
-// bf16 hi/lo split of an fp32 value: x ~= hi + lo with |x - hi - lo| <= 2^-17 |x|
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+// fp16 hi/lo split of an fp32 value: hi = fp16(x) (11-bit significand), lo = fp16(x - hi), so x ~= hi + lo with
+// |x - hi - lo| <= 2^-24 |x| while lo stays a normal fp16 number (|x| >~ 0.25) and <= 3e-8 absolute below that
+// (fp16 subnormal spacing) - fp32-grade for the O(1) activations / O(1e-2) weights of a BatchNorm ResNet.  The three
+// products hi*hi + hi*lo + lo*hi are exact in the fp32 accumulator; the dropped lo*lo term is <= 2^-24 relative.
+// Conversions saturate at +-65504 instead of overflowing to inf.
+__device__ __forceinline__ __half f16_sat(float x) {
+  unsigned short h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  return __ushort_as_half(h);
+}
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  hi = f16_sat(x);
+  lo = f16_sat(x - __half2float(hi));
 }
 #endif  // __CUDACC__
 

@@ -11,9 +11,9 @@
 //             filter taps read it through row-shifted UMMA descriptors (start address + (r*(W+2)+s)*128 B), cutting
 //             the L2->SM activation traffic ~4.7x versus im2col.  Positions x >= W of each padded row are computed
 //             and discarded.
-// Operands are bf16.  To reproduce the reference's fp32 arithmetic (torch conv2d / mm, SURVEY.md 7 "hard parts") every
-// fp32 value is carried as a bf16 (hi, lo) pair and each k-step issues three MMAs lo*hi + hi*lo + hi*hi into the same
-// accumulator ("bf16x3", passes = 3).  passes = 1 is plain bf16.
+// Operands are fp16.  To reproduce the reference's fp32 arithmetic (torch conv2d / mm, SURVEY.md 7 "hard parts") every
+// fp32 value is carried as a fp16 (hi, lo) pair and each k-step issues three MMAs lo*hi + hi*lo + hi*hi into the same
+// accumulator ("fp16x3", passes = 3).  passes = 1 is plain fp16.
 //
 // Warp roles (192 threads): warp 0 = TMA producer (separate A and B rings), warp 1 = TMEM allocator + MMA issuer,
 // warps 2..5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store; per-channel sum / sum-of-squares for
@@ -29,13 +29,14 @@
 namespace vb {
 
 constexpr int BM = 128;          // rows (output positions) per tile == UMMA M == TMEM lanes
-constexpr int BK = 64;           // bf16 elements per k-block        == one 128-byte swizzle row
-constexpr int UMMA_K = 16;       // bf16
+constexpr int BK = 64;           // fp16 elements per k-block        == one 128-byte swizzle row
+constexpr int UMMA_K = 16;       // fp16
 constexpr int GEMM_THREADS = 288;       // 4 TMA producer warps + 1 MMA warp + 4 epilogue warps
 constexpr int EPI_WARP0 = 5;            // first epilogue warp
 constexpr int EPI_TID0 = EPI_WARP0 * 32;
 constexpr int MAX_RING = 8;
 constexpr int STAGING_BYTES = BM * 128;   // 128 rows x 32 fp32
+constexpr size_t SMEM_BUDGET = 227 * 1024;
 
 struct GemmKernelParams {
   CUtensorMap a_hi, a_lo, b_hi, b_lo, out;
@@ -53,6 +54,7 @@ struct GemmKernelParams {
   const float* scale;
   const float* bias;
   int relu;
+  float alpha;                   // accumulators are multiplied by alpha first (exact power-of-two weight descale)
   double* stats;                 // optional [2][N]
   // train-mode BatchNorm finalize by the last CTA (all optional; need stats)
   const float* bn_gamma;
@@ -101,7 +103,9 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 // CG = 1: one CTA per 128-row tile.  CG = 2: a CTA pair (cluster of 2 on one TPC) computes a 256-row tile with
 // tcgen05.mma.cta_group::2 - the leader's single issuing thread drives both SMs' tensor cores, each CTA loads its own
 // 128 A rows and HALF of the weight tile, which halves both the MMA-dispatch load and the weight bytes per SM.
-template <int BN, int CG>
+// HALO selects the A-operand mode 2 code paths at compile time (the MMA-issuing thread is the critical resource:
+// its loop must carry no mode checks, divisions or 64-bit descriptor arithmetic).
+template <int BN, int CG, bool HALO>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B tiles
@@ -116,7 +120,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
   const int tile_step = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t a_stage_bytes = p.a_plane_bytes * planes;
   const uint32_t b_stage_bytes = B_TILE * planes;
-  const bool merged = (p.b_per_a == 1);            // A and B rings advance in lockstep and share barriers
+  constexpr bool merged = !HALO;                   // A and B rings advance in lockstep and share barriers
 
   uint8_t* a_ring = smem;
   uint8_t* b_ring = a_ring + (size_t)p.a_stages * a_stage_bytes;
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     }
     // "full" barriers: every CTA's TMA loads signal its OWN barrier (local complete_tx); in a pair the leader's
     // barrier takes one more arrival, forwarded by the peer's otherwise idle warp 1 once the peer's data has landed
-    // one arrival (with its expect_tx) per producer warp = per bf16 plane.  When every A load pairs with exactly
+    // one arrival (with its expect_tx) per producer warp = per fp16 plane.  When every A load pairs with exactly
     // one B load (tiled / im2col modes) both operands share the B ring's barriers: one wait per k-block.
     const uint32_t fwd = (CG == 2 && cta_rank == 0) ? 1u : 0u;
     for (int s = 0; s < p.a_stages; ++s) {
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
           const int q0 = rem - p0 * p.Q;
           ph = p0 * p.stride - p.pad_h;
           qw = q0 * p.stride - p.pad_w;
-        } else if (p.a_mode == 2) {
+        } else if (HALO) {
           img = m_blk / p.tiles_per_img;
           ph = (m_blk - img * p.tiles_per_img) * p.TH - 1;        // first halo row
         }
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             ++tr_p;
             uint8_t* dst = b_ring + (size_t)bs * b_stage_bytes + (size_t)plane * B_TILE;
             // weight k-block: modes 0/1 -> ac; halo -> tap bi, channel block ac
-            const int kb = (p.a_mode == 2) ? (bi * p.a_chunks + ac) : ac;
+            const int kb = HALO ? (bi * p.a_chunks + ac) : ac;
             if (elect_one()) {
               if (p.debug_skip_mma & 4) mbar_arrive(&b_full[bs]);
               else {
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     }
   } else if (warp == 4) {
     // ======================= MMA issuer (leader CTA only when CG == 2) =======================
-    constexpr uint32_t idesc = make_idesc(UMMA_FMT_BF16, BM * CG, BN);
+    constexpr uint32_t idesc = make_idesc(UMMA_FMT_F16, BM * CG, BN);
     int as = 0, bs = 0;
     uint32_t aphase = 0, bphase = 0;
     int local_t = 0;
@@ -306,6 +310,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         }
       }
     }
+    // ---- leader: the one thread per CTA (pair) that feeds the tensor cores ----
+    // Shared-memory matrix descriptors are handled as two 32-bit words: the high word (SBO = 1024 B, version 1,
+    // SWIZZLE_128B) is a constant, the low word is (address >> 4) | LBO(16 B) << 16; stepping to the next 16-element
+    // k-slice adds 2 to the low word.  Everything below is warp-uniform so it lives in uniform registers.
+    constexpr uint32_t DESC_HI = 0x40004040u;
+    const uint32_t a_ring_w = (smem_u32(a_ring) >> 4) | 0x10000u;
+    const uint32_t b_ring_w = (smem_u32(b_ring) >> 4) | 0x10000u;
+    const uint32_t a_stage_w = a_stage_bytes >> 4, a_plane_w = p.a_plane_bytes >> 4;
+    const uint32_t b_stage_w = b_stage_bytes >> 4;
+    constexpr uint32_t b_plane_w = B_TILE >> 4;
+    const uint32_t b_full0 = smem_u32(b_full), b_empty0 = smem_u32(b_empty);
+    const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty);
+    const bool skip_mma = (p.debug_skip_mma & 1) != 0;
+    const int a_chunks = p.a_chunks, a_stages = p.a_stages, b_stages = p.b_stages;
+    const uint32_t wp8 = (uint32_t)p.Wp * 8u;            // halo: one padded image row in descriptor units
     for (int tile = (cta_rank == 0 ? tile_start : num_tiles); tile < num_tiles; tile += tile_step, ++local_t) {
       const int acc = local_t & 1;
       const uint32_t acc_phase = (local_t >> 1) & 1;
@@ -313,65 +332,60 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * BN;
       uint32_t accumulate = 0;
-      for (int ac = 0; ac < p.a_chunks; ++ac) {
-        if (!merged) mbar_wait(&a_full[as], aphase);
-        const uint32_t a_hi0 = smem_u32(a_ring + (size_t)as * a_stage_bytes);
-        for (int bi = 0; bi < p.b_per_a; ++bi) {
-          mbar_wait(&b_full[bs], bphase);
+      for (int ac = 0; ac < a_chunks; ++ac) {
+        uint32_t a_w;
+        if (HALO) {
+          mbar_wait_addr(a_full0 + 8u * as, aphase);
+          a_w = a_ring_w + (uint32_t)as * a_stage_w;
+        }
+        const bool last_chunk = (ac == a_chunks - 1);
+        constexpr int TAPS = HALO ? 9 : 1;
+#pragma unroll
+        for (int bi = 0; bi < TAPS; ++bi) {
+          mbar_wait_addr(b_full0 + 8u * bs, bphase);
           tc_fence_after_sync();
           if (lane == 0) VB_TRACE_EVENT(1, tr_m);
           // halo mode: filter tap (r, s) = rows shifted by r*(W+2)+s inside the halo tile
-          const uint32_t a_off = (p.a_mode == 2) ? (uint32_t)((bi / 3) * p.Wp + (bi % 3)) * 128u : 0u;
-          const uint32_t b_hi = smem_u32(b_ring + (size_t)bs * b_stage_bytes);
-          // descriptors of the first k-step; the next ones advance the 16-byte-unit start address by 2 (32 bytes)
-          const uint64_t da_hi0 = make_smem_desc(a_hi0 + a_off, 16, 1024, UMMA_LAYOUT_SW128);
-          const uint64_t da_lo0 = make_smem_desc(a_hi0 + a_off + p.a_plane_bytes, 16, 1024, UMMA_LAYOUT_SW128);
-          const uint64_t db_hi0 = make_smem_desc(b_hi, 16, 1024, UMMA_LAYOUT_SW128);
-          const uint64_t db_lo0 = make_smem_desc(b_hi + B_TILE, 16, 1024, UMMA_LAYOUT_SW128);
+          const uint32_t aw = HALO ? a_w + (uint32_t)(bi / 3) * wp8 + (uint32_t)(bi % 3) * 8u
+                                   : a_ring_w + (uint32_t)bs * a_stage_w;
+          const uint32_t bw = b_ring_w + (uint32_t)bs * b_stage_w;
           if (elect_one()) {
+            if (!skip_mma) {
+              if (planes == 2) {
 #pragma unroll
-            for (int k = 0; k < ((p.debug_skip_mma & 1) ? 0 : BK / UMMA_K); ++k) {
-              const uint64_t kadv = (uint64_t)(k * UMMA_K * 2 / 16);
-              if (CG == 2) {
-                if (planes == 2) {
-                  umma2_bf16(d_tmem, da_lo0 + kadv, db_hi0 + kadv, idesc, accumulate);
-                  umma2_bf16(d_tmem, da_hi0 + kadv, db_lo0 + kadv, idesc, 1);
-                  umma2_bf16(d_tmem, da_hi0 + kadv, db_hi0 + kadv, idesc, 1);
-                } else {
-                  umma2_bf16(d_tmem, da_hi0 + kadv, db_hi0 + kadv, idesc, accumulate);
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                  // small cross terms first, dominant term last
+                  umma_f16_w<CG>(d_tmem, aw + a_plane_w + 2 * k, bw + 2 * k, DESC_HI, idesc, accumulate);
+                  umma_f16_w<CG>(d_tmem, aw + 2 * k, bw + b_plane_w + 2 * k, DESC_HI, idesc, 1);
+                  umma_f16_w<CG>(d_tmem, aw + 2 * k, bw + 2 * k, DESC_HI, idesc, 1);
+                  accumulate = 1;
                 }
-              } else if (planes == 2) {
-                // small cross terms first, dominant term last
-                umma_bf16(d_tmem, da_lo0 + kadv, db_hi0 + kadv, idesc, accumulate);
-                umma_bf16(d_tmem, da_hi0 + kadv, db_lo0 + kadv, idesc, 1);
-                umma_bf16(d_tmem, da_hi0 + kadv, db_hi0 + kadv, idesc, 1);
               } else {
-                umma_bf16(d_tmem, da_hi0 + kadv, db_hi0 + kadv, idesc, accumulate);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                  umma_f16_w<CG>(d_tmem, aw + 2 * k, bw + 2 * k, DESC_HI, idesc, accumulate);
+                  accumulate = 1;
+                }
               }
-              accumulate = 1;
             }
-            const bool last_b = (bi == p.b_per_a - 1);
-            if (CG == 2) {
-              umma2_commit_multicast(&b_empty[bs]);                        // frees the weight slot in BOTH CTAs
-              if (last_b && !merged) umma2_commit_multicast(&a_empty[as]); // ... the activation slot after its last tap
-              if (last_b && ac == p.a_chunks - 1) umma2_commit_multicast(&tmem_full[acc]);   // accumulators ready
-            } else {
-              umma_commit(&b_empty[bs]);           // frees the weight slot when these MMAs retire
-              if (last_b && !merged) umma_commit(&a_empty[as]);
-              if (last_b && ac == p.a_chunks - 1) umma_commit(&tmem_full[acc]);
-            }
+            const bool last_b = (bi == TAPS - 1);
+            umma_commit_addr<CG>(b_empty0 + 8u * bs);                 // frees the weight slot (in BOTH CTAs of a pair)
+            if (HALO && last_b) umma_commit_addr<CG>(a_empty0 + 8u * as);   // ... the halo slot after its last tap
+            if (last_b && last_chunk) umma_commit_addr<CG>(smem_u32(&tmem_full[acc]));   // accumulators ready
           }
           accumulate = 1;
           if (lane == 0) VB_TRACE_EVENT(2, tr_m);
           ++tr_m;
-          if (++bs == p.b_stages) {
+          if (++bs == b_stages) {
             bs = 0;
             bphase ^= 1;
           }
         }
-        if (++as == p.a_stages) {
-          as = 0;
-          aphase ^= 1;
+        if (HALO) {
+          if (++as == a_stages) {
+            as = 0;
+            aphase ^= 1;
+          }
         }
       }
     }
@@ -383,7 +397,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     const bool store_leader = (etid == 0);
     // halo mode: which output pixel (if any) this accumulator row is
     int hy = 0, hx = 0;
-    if (p.a_mode == 2) {
+    if (HALO) {
       hy = row / p.Wp;
       hx = row - hy * p.Wp;
     }
@@ -403,7 +417,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       int img = 0, y0 = 0;
       bool valid = true;
       int srow = row;                              // row inside the staging tile
-      if (p.a_mode == 2) {
+      if (HALO) {
         img = m_blk / p.tiles_per_img;
         y0 = (m_blk - img * p.tiles_per_img) * p.TH;
         valid = (hy < p.TH) && (hx < p.W) && (y0 + hy < p.H);
@@ -451,7 +465,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         }
         float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = valid ? __uint_as_float(raw[i]) : 0.f;
+        for (int i = 0; i < 32; ++i) v[i] = valid ? __uint_as_float(raw[i]) * p.alpha : 0.f;
         const int c0 = n_blk * BN + chunk * 32;
         if (p.stats != nullptr) {
           // butterfly transpose-reduce: afterwards lane L holds the sum over the warp's 32 rows of channel c0+L
@@ -503,7 +517,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
         if (store_leader) {
-          if (p.a_mode == 2) tma_store_4d(&p.out, staging, c0, 0, y0, img);
+          if (HALO) tma_store_4d(&p.out, staging, c0, 0, y0, img);
           else tma_store_2d(&p.out, staging, c0, m_blk * BM);
           tma_store_commit();
         }
@@ -600,16 +614,20 @@ static int num_sms() {
   return g_num_sms;
 }
 
-constexpr size_t SMEM_BUDGET = 227 * 1024;
 static size_t fixed_smem(int bn) {
   return 1024 /*align slack*/ + STAGING_BYTES + (4 * MAX_RING + 4) * 8 + 16 + 8 * bn * 8;
 }
 
-template <int BN, int CG>
+template <int BN, int CG, bool HALO>
 static int launch_gemm(const GemmKernelParams& kp, size_t smem, int grid, cudaStream_t stream) {
-  VB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (CG == 1 && !getenv("VINCE_B200_CLUSTER_ONLY")) {
-    conv_gemm_kernel<BN, CG><<<grid, GEMM_THREADS, smem, stream>>>(kp);
+  static size_t smem_set = 0;                        // per instantiation: the opt-in only ever needs to grow
+  if (smem > smem_set) {
+    VB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, CG, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)SMEM_BUDGET));
+    smem_set = SMEM_BUDGET;
+  }
+  if (CG == 1) {
+    conv_gemm_kernel<BN, CG, HALO><<<grid, GEMM_THREADS, smem, stream>>>(kp);
   } else {
     grid &= ~1;
     cudaLaunchConfig_t cfg;
@@ -625,7 +643,7 @@ static int launch_gemm(const GemmKernelParams& kp, size_t smem, int grid, cudaSt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CG>, kp));
+    VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CG, HALO>, kp));
   }
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
@@ -685,7 +703,7 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   VB_REQUIRE(d.N % 32 == 0, "conv_gemm: N=%d must be a multiple of 32", d.N);
   VB_REQUIRE(d.passes == 1 || d.passes == 3, "conv_gemm: passes must be 1 or 3");
   VB_REQUIRE(d.a_hi && d.b_hi && d.out, "conv_gemm: null operand");
-  VB_REQUIRE(d.passes == 1 || (d.a_lo && d.b_lo), "conv_gemm: bf16x3 needs lo planes");
+  VB_REQUIRE(d.passes == 1 || (d.a_lo && d.b_lo), "conv_gemm: fp16x3 needs lo planes");
   VB_REQUIRE(!(d.stats && (d.bias || d.scale || d.relu)), "conv_gemm: stats are defined on raw accumulators only");
   VB_REQUIRE(!d.bn_coef || (d.stats && d.bn_gamma && d.bn_beta && d.bn_running_mean && d.bn_running_var && d.bn_counter),
              "conv_gemm: BatchNorm finalize needs stats, gamma, beta, running stats and a counter");
@@ -710,6 +728,7 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   kp.scale = d.scale;
   kp.bias = d.bias;
   kp.relu = d.relu;
+  kp.alpha = d.alpha != 0.f ? d.alpha : 1.f;
   kp.stats = d.stats;
   kp.bn_gamma = d.bn_gamma, kp.bn_beta = d.bn_beta, kp.bn_running_mean = d.bn_running_mean;
   kp.bn_running_var = d.bn_running_var, kp.bn_nbt = reinterpret_cast<long long*>(d.bn_num_batches_tracked);
@@ -743,11 +762,11 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
     const uint32_t halo_rows = (uint32_t)(th + 2) * Wp;
     kp.a_tx_bytes = halo_rows * 128;
     kp.a_plane_bytes = ((halo_rows + 7) / 8) * 1024;
-    rc = encode_tma_4d_nhwc(&kp.a_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d.a_hi, d.batch, d.H, d.W, d.Cin, BK, Wp, th + 2,
+    rc = encode_tma_4d_nhwc(&kp.a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.a_hi, d.batch, d.H, d.W, d.Cin, BK, Wp, th + 2,
                             CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     if (d.passes == 3) {
-      rc = encode_tma_4d_nhwc(&kp.a_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d.a_lo, d.batch, d.H, d.W, d.Cin, BK, Wp,
+      rc = encode_tma_4d_nhwc(&kp.a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.a_lo, d.batch, d.H, d.W, d.Cin, BK, Wp,
                               th + 2, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }
@@ -764,33 +783,33 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
     kp.pad_h = d.pad_lo_h;
     kp.pad_w = d.pad_lo_w;
     kp.S = d.S;
-    rc = encode_tma_im2col_nhwc(&kp.a_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d.a_hi, d.batch, d.H, d.W, d.Cin, d.pad_lo_h,
+    rc = encode_tma_im2col_nhwc(&kp.a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.a_hi, d.batch, d.H, d.W, d.Cin, d.pad_lo_h,
                                 d.pad_lo_w, d.pad_hi_h, d.pad_hi_w, d.R, d.S, d.stride, BK, BM,
-                                CU_TENSOR_MAP_SWIZZLE_128B);
+                                CU_TENSOR_MAP_SWIZZLE_128B, d.a_pixel_stride, d.a_row_stride, d.a_img_stride);
     if (rc) return rc;
     if (d.passes == 3) {
-      rc = encode_tma_im2col_nhwc(&kp.a_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d.a_lo, d.batch, d.H, d.W, d.Cin,
+      rc = encode_tma_im2col_nhwc(&kp.a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.a_lo, d.batch, d.H, d.W, d.Cin,
                                   d.pad_lo_h, d.pad_lo_w, d.pad_hi_h, d.pad_hi_w, d.R, d.S, d.stride, BK, BM,
-                                  CU_TENSOR_MAP_SWIZZLE_128B);
+                                  CU_TENSOR_MAP_SWIZZLE_128B, d.a_pixel_stride, d.a_row_stride, d.a_img_stride);
       if (rc) return rc;
     }
   } else {
     kp.a_mode = 0;
-    rc = encode_tma_2d(&kp.a_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d.a_hi, d.K, d.M, (uint64_t)d.K * 2, BK, BM,
+    rc = encode_tma_2d(&kp.a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.a_hi, d.K, d.M, (uint64_t)d.K * 2, BK, BM,
                        CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     if (d.passes == 3) {
-      rc = encode_tma_2d(&kp.a_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d.a_lo, d.K, d.M, (uint64_t)d.K * 2, BK, BM,
+      rc = encode_tma_2d(&kp.a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.a_lo, d.K, d.M, (uint64_t)d.K * 2, BK, BM,
                          CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }
   }
   // each CTA of a pair loads its half of the weight tile
-  rc = encode_tma_2d(&kp.b_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d.b_hi, d.K, d.N, (uint64_t)d.K * 2, BK, bn / cg,
+  rc = encode_tma_2d(&kp.b_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.b_hi, d.K, d.N, (uint64_t)d.K * 2, BK, bn / cg,
                      CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   if (d.passes == 3) {
-    rc = encode_tma_2d(&kp.b_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d.b_lo, d.K, d.N, (uint64_t)d.K * 2, BK, bn / cg,
+    rc = encode_tma_2d(&kp.b_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.b_lo, d.K, d.N, (uint64_t)d.K * 2, BK, bn / cg,
                        CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
@@ -821,15 +840,14 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   const int tiles = kp.num_m_blocks * kp.num_n_blocks;
   int grid = tiles * cg < num_sms() ? tiles * cg : num_sms();
   if (getenv("VINCE_B200_DEBUG_GRID") && atoi(getenv("VINCE_B200_DEBUG_GRID")) < grid) grid = atoi(getenv("VINCE_B200_DEBUG_GRID"));
-  if (cg == 2) {
-    grid &= ~1;
-    if (bn == 64) return launch_gemm<64, 2>(kp, smem, grid, stream);
-    if (bn == 128) return launch_gemm<128, 2>(kp, smem, grid, stream);
-    return launch_gemm<256, 2>(kp, smem, grid, stream);
-  }
-  if (bn == 64) return launch_gemm<64, 1>(kp, smem, grid, stream);
-  if (bn == 128) return launch_gemm<128, 1>(kp, smem, grid, stream);
-  return launch_gemm<256, 1>(kp, smem, grid, stream);
+  const bool halo = kp.a_mode == 2;
+  if (cg == 2) grid &= ~1;
+#define VB_LAUNCH(BN_, CG_)                                                              \
+  if (bn == BN_ && cg == CG_)                                                            \
+    return halo ? launch_gemm<BN_, CG_, true>(kp, smem, grid, stream) : launch_gemm<BN_, CG_, false>(kp, smem, grid, stream);
+  VB_LAUNCH(64, 1) VB_LAUNCH(128, 1) VB_LAUNCH(256, 1) VB_LAUNCH(64, 2) VB_LAUNCH(128, 2) VB_LAUNCH(256, 2)
+#undef VB_LAUNCH
+  VB_REQUIRE(false, "conv_gemm: no kernel for bn=%d cg=%d", bn, cg);
 }
 
 }  // namespace vb

@@ -1,6 +1,8 @@
 // HBM-bound kernels of the encoder + queue path: layout packing, weight preparation, train/eval BatchNorm apply
-// (+ReLU, +residual, +max/avg pooling), bf16 hi/lo splitting, L2 normalisation, jigsaw gathers, and the fused
+// (+ReLU, +residual, +max/avg pooling), fp16 hi/lo splitting, L2 normalisation, jigsaw gathers, and the fused
 // multi-tensor momentum-EMA + ring-buffer enqueue.  All are coalesced, vectorised (16-byte) streaming kernels.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -8,92 +10,92 @@ namespace vb {
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-struct alignas(8) bf16x4 {
-  __nv_bfloat16 v[4];
+struct alignas(8) h16x4 {
+  __half v[4];
 };
-struct alignas(16) bf16x8 {
-  __nv_bfloat16 v[8];
+struct alignas(16) h16x8 {
+  __half v[8];
 };
 
-__device__ __forceinline__ void split4(const float4& f, bf16x4& hi, bf16x4& lo) {
-  split_bf16(f.x, hi.v[0], lo.v[0]);
-  split_bf16(f.y, hi.v[1], lo.v[1]);
-  split_bf16(f.z, hi.v[2], lo.v[2]);
-  split_bf16(f.w, hi.v[3], lo.v[3]);
+__device__ __forceinline__ void split4(const float4& f, h16x4& hi, h16x4& lo) {
+  split_f16(f.x, hi.v[0], lo.v[0]);
+  split_f16(f.y, hi.v[1], lo.v[1]);
+  split_f16(f.z, hi.v[2], lo.v[2]);
+  split_f16(f.w, hi.v[3], lo.v[3]);
 }
-__device__ __forceinline__ float4 join4(const bf16x4& hi, const bf16x4& lo) {
-  return make_float4(__bfloat162float(hi.v[0]) + __bfloat162float(lo.v[0]),
-                     __bfloat162float(hi.v[1]) + __bfloat162float(lo.v[1]),
-                     __bfloat162float(hi.v[2]) + __bfloat162float(lo.v[2]),
-                     __bfloat162float(hi.v[3]) + __bfloat162float(lo.v[3]));
+__device__ __forceinline__ float4 join4(const h16x4& hi, const h16x4& lo) {
+  return make_float4(__half2float(hi.v[0]) + __half2float(lo.v[0]),
+                     __half2float(hi.v[1]) + __half2float(lo.v[1]),
+                     __half2float(hi.v[2]) + __half2float(lo.v[2]),
+                     __half2float(hi.v[3]) + __half2float(lo.v[3]));
 }
 
 // ------------------------------------------------------------------------------------------------
-// stem packing: one block per (image n, row pair j).  The six input rows (2 image rows x 3 channels) are staged
-// in shared memory with coalesced loads (every input row belongs to exactly one j, so the image is read once),
-// then each thread emits 16-byte groups of the 64-element packed "pixel" for consecutive q.
+// stem packing (overlapping-window layout): X[n, a, b, 16] holds the 2x2x3 input patch of row pair a-2 and column
+// pair b-2:  X[n,a,b,(dr*2+dc)*3+c] = x[idx[n], c, 2(a-2)+dr, 2(b-2)+dc]  (0 outside the image, 0 for e >= 12).
+// The 64 contiguous elements starting at (a, b = q) are then exactly the 2 x 8 x 3 input window (rows 2a-4, 2a-3,
+// columns 2q-4 .. 2q+3) that output column q needs from that row pair, so the conv kernel's TMA descriptor reads
+// 64-"channel" pixels at a pixel stride of 16 elements: the packed tensor is 1.4x the image instead of 5.4x.
+// One block per (image n, row pair a): the six input rows are staged in shared memory with coalesced loads.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(128) stem_pack_kernel(const float* __restrict__ x,
                                                         const int64_t* __restrict__ gather_idx,
-                                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                                        int H, int W, int Hj, int Q) {
-  extern __shared__ float rows[];                 // [6][W + 6], 3 zero columns of left padding
-  __shared__ int lut[64];                         // element e -> offset of (r2, c, s) inside `rows`, or -1
-  const int j = blockIdx.x;
+                                                        __half* __restrict__ hi, __half* __restrict__ lo,
+                                                        int H, int W, int Ha, int Wb) {
+  extern __shared__ float rows[];                 // [2 dr][3 c][W]
+  const int a = blockIdx.x;
   const int n = blockIdx.y;
-  const int Wp = W + 6;
   const int tid = threadIdx.x;
-  if (tid < 64) {
-    int off = -1;
-    if (tid < 42) {
-      const int r2 = tid / 21, rem = tid - r2 * 21, s = rem / 3, c = rem - s * 3;
-      off = (r2 * 3 + c) * Wp + s;
-    }
-    lut[tid] = off;
-  }
   const int64_t src_n = gather_idx ? gather_idx[n] : n;
   const float* xn = x + src_n * 3 * (int64_t)H * W;
-  for (int i = tid; i < 6 * Wp; i += blockDim.x) {
-    const int rc = i / Wp, col = i - rc * Wp - 3;
-    const int r2 = rc / 3, c = rc - r2 * 3;
-    const int row = 2 * j - 1 + r2;
-    float v = 0.f;
-    if (row >= 0 && row < H && col >= 0 && col < W) v = __ldg(xn + ((int64_t)c * H + row) * W + col);
-    rows[i] = v;
+  const int row0 = 2 * (a - 2);
+  for (int i = tid; i < 6 * W; i += blockDim.x) {
+    const int rc = i / W, col = i - rc * W;
+    const int dr = rc / 3, c = rc - dr * 3;
+    const int row = row0 + dr;
+    rows[i] = (row >= 0 && row < H) ? __ldg(xn + ((int64_t)c * H + row) * W + col) : 0.f;
   }
   __syncthreads();
-  const int64_t base = (((int64_t)n * Hj + j) * Q) * 64;
-  for (int g = tid; g < Q * 8; g += blockDim.x) {
-    const int q = g >> 3, grp = g & 7;
-    bf16x8 oh, ol;
+  const int64_t base = (((int64_t)n * Ha + a) * Wb) * 16;
+  for (int b = tid; b < Wb; b += blockDim.x) {
+    const int col0 = 2 * (b - 2);
+    h16x8 oh[2], ol[2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int off = lut[grp * 8 + i];
-      const float val = off >= 0 ? rows[off + 2 * q] : 0.f;
-      split_bf16(val, oh.v[i], ol.v[i]);
+    for (int e = 0; e < 16; ++e) {
+      float val = 0.f;
+      if (e < 12) {
+        const int dr = e / 6, dc = (e % 6) / 3, c = e % 3;
+        const int col = col0 + dc;
+        if (col >= 0 && col < W) val = rows[(dr * 3 + c) * W + col];
+      }
+      split_f16(val, oh[e >> 3].v[e & 7], ol[e >> 3].v[e & 7]);
     }
-    *reinterpret_cast<bf16x8*>(hi + base + (int64_t)g * 8) = oh;
-    if (lo) *reinterpret_cast<bf16x8*>(lo + base + (int64_t)g * 8) = ol;
+    h16x8* dh = reinterpret_cast<h16x8*>(hi + base + (int64_t)b * 16);
+    dh[0] = oh[0], dh[1] = oh[1];
+    if (lo) {
+      h16x8* dl = reinterpret_cast<h16x8*>(lo + base + (int64_t)b * 16);
+      dl[0] = ol[0], dl[1] = ol[1];
+    }
   }
 }
 
-int stem_pack_launch(const float* x, const int64_t* gather_idx, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int H,
-                     int W, int Hj, int Q, cudaStream_t stream) {
+int stem_pack_launch(const float* x, const int64_t* gather_idx, __half* hi, __half* lo, int N, int H,
+                     int W, int Ha, int Wb, cudaStream_t stream) {
   if (N == 0) return VB_OK;
   VB_REQUIRE(N <= 65535, "stem_pack: batch %d too large", N);
-  const size_t smem = (size_t)6 * (W + 6) * sizeof(float);
+  const size_t smem = (size_t)6 * W * sizeof(float);
   VB_REQUIRE(smem <= 48 * 1024, "stem_pack: image width %d too large", W);
-  dim3 grid(Hj, N);
-  stem_pack_kernel<<<grid, 256, smem, stream>>>(x, gather_idx, hi, lo, H, W, Hj, Q);
+  dim3 grid(Ha, N);
+  stem_pack_kernel<<<grid, 128, smem, stream>>>(x, gather_idx, hi, lo, H, W, Ha, Wb);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight preparation: OIHW fp32 -> K-major [Cout][R][S][Cin] bf16 hi/lo (or the packed stem layout)
+// weight preparation: OIHW fp32 -> K-major [Cout][R][S][Cin] fp16 hi/lo (or the packed stem layout)
 // ------------------------------------------------------------------------------------------------
-__global__ void weight_prep_kernel(const WeightPrepEntry* __restrict__ table, __nv_bfloat16* __restrict__ hi,
-                                   __nv_bfloat16* __restrict__ lo) {
+__global__ void weight_prep_kernel(const WeightPrepEntry* __restrict__ table, __half* __restrict__ hi,
+                                   __half* __restrict__ lo) {
   const WeightPrepEntry e = table[blockIdx.y];
   const int64_t K = e.kind == 1 ? 256 : (int64_t)e.R * e.S * e.Cin;
   const int64_t total = (int64_t)e.Cout * K;
@@ -106,27 +108,26 @@ __global__ void weight_prep_kernel(const WeightPrepEntry* __restrict__ table, __
       const int ci = k - rs * e.Cin;
       w = __ldg(e.src + ((int64_t)co * e.Cin + ci) * (e.R * e.S) + rs);
     } else {
-      // stem: k = t*64 + r2*21 + s*3 + c  <-  w[co, c, r = 2t + r2, s]   (7x7, Cin = 3)
+      // stem: k = t*64 + j*16 + (dr*2+dc)*3 + c  <-  w[co, c, r = 2t+dr-1, s = 2j+dc-1]   (7x7, Cin = 3):
+      // tap t is the row pair p-2+t, j the column pair q-2+j of output pixel (p, q) (see stem_pack_kernel)
       const int t = k >> 6;
-      const int el = k & 63;
-      if (el < 42) {
-        const int r2 = el / 21;
-        const int rem = el - r2 * 21;
-        const int s = rem / 3;
-        const int c = rem - s * 3;
-        const int r = 2 * t + r2;
-        if (r < 7) w = __ldg(e.src + (((int64_t)co * 3 + c) * 7 + r) * 7 + s);
+      const int j = (k >> 4) & 3;
+      const int el = k & 15;
+      if (el < 12) {
+        const int dr = el / 6, dc = (el % 6) / 3, c = el % 3;
+        const int r = 2 * t + dr - 1, sx = 2 * j + dc - 1;
+        if (r >= 0 && r < 7 && sx >= 0 && sx < 7) w = __ldg(e.src + (((int64_t)co * 3 + c) * 7 + r) * 7 + sx);
       }
     }
-    __nv_bfloat16 h, l;
-    split_bf16(w, h, l);
+    __half h, l;
+    split_f16(ldexpf(w, e.scale_log2), h, l);
     hi[e.dst_off + i] = h;
     if (lo) lo[e.dst_off + i] = l;
   }
 }
 
-int weight_prep_launch(const WeightPrepEntry* table_dev, int n_entries, int64_t max_elems, __nv_bfloat16* hi,
-                       __nv_bfloat16* lo, cudaStream_t stream) {
+int weight_prep_launch(const WeightPrepEntry* table_dev, int n_entries, int64_t max_elems, __half* hi,
+                       __half* lo, cudaStream_t stream) {
   if (n_entries == 0) return VB_OK;
   int bx = div_up(max_elems, 256 * 8);
   if (bx > 1024) bx = 1024;
@@ -169,132 +170,214 @@ __device__ __forceinline__ float4 max4(const float4& a, const float4& b) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// bn_apply: out = relu?( bn(main) + residual )  ->  bf16 hi/lo planes (and/or fp32)
-// thread t owns channel group (t % C4) and strides over rows; total threads is a multiple of C4.
+// bn_apply: out = relu?( bn(main) + residual )  ->  fp16 hi/lo planes (and/or fp32)
+// A thread owns V (4 or 8) consecutive channels of a row.  A block works on contiguous tiles of
+// (blockDim / (C/V)) * U rows: all U rows' loads are issued before any arithmetic (memory-level parallelism), and a
+// tile is one contiguous span of every tensor (DRAM page locality).  Tiles are handed out grid-strided.
 // ------------------------------------------------------------------------------------------------
-__global__ void bn_apply_kernel(BnSideDev main, int res_kind, const __nv_bfloat16* __restrict__ res_hi,
-                                const __nv_bfloat16* __restrict__ res_lo, BnSideDev res_bn, int relu,
-                                __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
-                                float* __restrict__ out_f32, int64_t M, int C) {
-  const int C4 = C >> 2;
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t gthreads = (int64_t)gridDim.x * blockDim.x;
-  const int cg = (int)(gtid % C4);
-  const int64_t row0 = gtid / C4;
-  const int64_t row_stride = gthreads / C4;
-  const int c = cg * 4;
-  float4 sc, sh, rsc, rsh;
-  bn_coeffs4(main, c, C, sc, sh);
-  if (res_kind == 2) bn_coeffs4(res_bn, c, C, rsc, rsh);
-  for (int64_t r = row0; r < M; r += row_stride) {
-    const int64_t off = r * C + c;
-    float4 v = fma4(__ldcs(reinterpret_cast<const float4*>(main.raw + off)), sc, sh);
-    if (res_kind == 1) {
-      const bf16x4 h = *reinterpret_cast<const bf16x4*>(res_hi + off);
-      bf16x4 l;
-      if (res_lo) l = *reinterpret_cast<const bf16x4*>(res_lo + off);
-      else l.v[0] = l.v[1] = l.v[2] = l.v[3] = __float2bfloat16_rn(0.f);
-      v = add4(v, join4(h, l));
-    } else if (res_kind == 2) {
-      v = add4(v, fma4(__ldcs(reinterpret_cast<const float4*>(res_bn.raw + off)), rsc, rsh));
+template <int V>
+struct VecF {
+  float4 q[V / 4];
+};
+template <int V>
+struct alignas(V * 2) VecH {
+  __half v[V];
+};
+
+template <int V, int U, int RES>
+__global__ void __launch_bounds__(256) bn_apply_kernel(BnSideDev main, const __half* __restrict__ res_hi,
+                                                       const __half* __restrict__ res_lo, BnSideDev res_bn, int relu,
+                                                       __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                                       float* __restrict__ out_f32, int64_t M, int C) {
+  const int CV = C / V;                               // threads per row
+  const int rows_per_pass = blockDim.x / CV;          // rows covered by the block at once (>= 1: checked on the host)
+  const int cg = threadIdx.x % CV;
+  const int lrow = threadIdx.x / CV;
+  const int c = cg * V;
+  float sc[V], sh[V], rsc[V], rsh[V];
+#pragma unroll
+  for (int i = 0; i < V; i += 4) {
+    float4 a, b;
+    bn_coeffs4(main, c + i, C, a, b);
+    sc[i] = a.x, sc[i + 1] = a.y, sc[i + 2] = a.z, sc[i + 3] = a.w;
+    sh[i] = b.x, sh[i + 1] = b.y, sh[i + 2] = b.z, sh[i + 3] = b.w;
+    if (RES == 2) {
+      bn_coeffs4(res_bn, c + i, C, a, b);
+      rsc[i] = a.x, rsc[i + 1] = a.y, rsc[i + 2] = a.z, rsc[i + 3] = a.w;
+      rsh[i] = b.x, rsh[i + 1] = b.y, rsh[i + 2] = b.z, rsh[i + 3] = b.w;
     }
-    if (relu) v = relu4(v);
-    if (out_hi) {
-      bf16x4 h, l;
-      split4(v, h, l);
-      *reinterpret_cast<bf16x4*>(out_hi + off) = h;
-      if (out_lo) *reinterpret_cast<bf16x4*>(out_lo + off) = l;
+  }
+  const int64_t tile_rows = (int64_t)rows_per_pass * U;
+  for (int64_t t0 = (int64_t)blockIdx.x * tile_rows; t0 < M; t0 += (int64_t)gridDim.x * tile_rows) {
+    VecF<V> raw[U], rres[U];
+    VecH<V> rh[U], rl[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = t0 + (int64_t)u * rows_per_pass + lrow;
+      if (rr < M) {
+        const int64_t off = rr * C + c;
+#pragma unroll
+        for (int i = 0; i < V / 4; ++i) raw[u].q[i] = __ldcs(reinterpret_cast<const float4*>(main.raw + off) + i);
+        if (RES == 1) {
+          rh[u] = *reinterpret_cast<const VecH<V>*>(res_hi + off);
+          if (res_lo) rl[u] = *reinterpret_cast<const VecH<V>*>(res_lo + off);
+        } else if (RES == 2) {
+#pragma unroll
+          for (int i = 0; i < V / 4; ++i) rres[u].q[i] = __ldcs(reinterpret_cast<const float4*>(res_bn.raw + off) + i);
+        }
+      }
     }
-    if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = v;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = t0 + (int64_t)u * rows_per_pass + lrow;
+      if (rr < M) {
+        const int64_t off = rr * C + c;
+        float v[V];
+        const float* rp = reinterpret_cast<const float*>(&raw[u]);
+        const float* rq = reinterpret_cast<const float*>(&rres[u]);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          v[i] = fmaf(rp[i], sc[i], sh[i]);
+          if (RES == 1) v[i] += __half2float(rh[u].v[i]) + (res_lo ? __half2float(rl[u].v[i]) : 0.f);
+          if (RES == 2) v[i] += fmaf(rq[i], rsc[i], rsh[i]);
+          if (relu) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (out_hi) {
+          VecH<V> h, l;
+#pragma unroll
+          for (int i = 0; i < V; ++i) split_f16(v[i], h.v[i], l.v[i]);
+          *reinterpret_cast<VecH<V>*>(out_hi + off) = h;
+          if (out_lo) *reinterpret_cast<VecH<V>*>(out_lo + off) = l;
+        }
+        if (out_f32) {
+#pragma unroll
+          for (int i = 0; i < V / 4; ++i)
+            reinterpret_cast<float4*>(out_f32 + off)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+      }
+    }
   }
 }
 
-static int elementwise_grid(int64_t work_threads, int C4, int threads) {
-  // a grid whose total thread count is a multiple of C4 (lcm handling: threads=256, C4 is a power of two <= 512
-  // for every ResNet width; otherwise fall back to one row per C4 threads with padding handled by the caller)
-  int64_t blocks = (work_threads + threads - 1) / threads;
-  const int64_t cap = 148 * 16;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  // make blocks*threads a multiple of C4
-  int64_t unit = C4 / threads;       // blocks must be a multiple of this when C4 > threads
-  if (unit > 1) blocks = ((blocks + unit - 1) / unit) * unit;
-  return (int)blocks;
+template <int V, int U>
+static void bn_apply_dispatch(int res_kind, int blocks, int threads, cudaStream_t stream, BnSideDev main,
+                              const __half* res_hi, const __half* res_lo, BnSideDev res_bn, int relu, __half* out_hi,
+                              __half* out_lo, float* out_f32, int64_t M, int C) {
+  if (res_kind == 0)
+    bn_apply_kernel<V, U, 0><<<blocks, threads, 0, stream>>>(main, res_hi, res_lo, res_bn, relu, out_hi, out_lo, out_f32, M, C);
+  else if (res_kind == 1)
+    bn_apply_kernel<V, U, 1><<<blocks, threads, 0, stream>>>(main, res_hi, res_lo, res_bn, relu, out_hi, out_lo, out_f32, M, C);
+  else
+    bn_apply_kernel<V, U, 2><<<blocks, threads, 0, stream>>>(main, res_hi, res_lo, res_bn, relu, out_hi, out_lo, out_f32, M, C);
 }
 
-int bn_apply_launch(const BnSide& main, int res_kind, const __nv_bfloat16* res_hi, const __nv_bfloat16* res_lo,
-                    const BnSide& res_bn, int relu, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, float* out_f32,
+int bn_apply_launch(const BnSide& main, int res_kind, const __half* res_hi, const __half* res_lo,
+                    const BnSide& res_bn, int relu, __half* out_hi, __half* out_lo, float* out_f32,
                     int64_t M, int C, cudaStream_t stream) {
   VB_REQUIRE(C % 4 == 0, "bn_apply: C=%d must be a multiple of 4", C);
-  const int C4 = C / 4;
-  const int threads = 256;
-  VB_REQUIRE((C4 <= threads && threads % C4 == 0) || (C4 > threads && C4 % threads == 0),
-             "bn_apply: unsupported channel count %d", C);
   if (M == 0) return VB_OK;
-  const int blocks = elementwise_grid(M * C4, C4, threads);
-  bn_apply_kernel<<<blocks, threads, 0, stream>>>(to_dev(main), res_kind, res_hi, res_lo, to_dev(res_bn), relu, out_hi,
-                                                  out_lo, out_f32, M, C);
+  // tuning knobs (debug): VINCE_B200_BNAPPLY = "<V><U>" e.g. "84" = 8 channels per thread, 4 rows in flight
+  static int cfg = -1;
+  if (cfg < 0) {
+    const char* e = getenv("VINCE_B200_BNAPPLY");
+    cfg = e ? atoi(e) : 82;
+  }
+  int V = cfg / 10, U = cfg % 10;
+  if (C % 8 != 0 || C / 8 > 256) V = 4;
+  const int threads = 256;
+  const int CV = C / V;
+  VB_REQUIRE(CV <= threads && threads % CV == 0, "bn_apply: unsupported channel count %d", C);
+  const int64_t tile_rows = (int64_t)(threads / CV) * U;
+  int64_t blocks = (M + tile_rows - 1) / tile_rows;
+  const int64_t cap = 148 * 8;
+  if (blocks > cap) blocks = cap;
+  const BnSideDev m = to_dev(main), r = to_dev(res_bn);
+#define VB_BN_CASE(v, u)                                                                                        \
+  if (V == v && U == u) {                                                                                       \
+    bn_apply_dispatch<v, u>(res_kind, (int)blocks, threads, stream, m, res_hi, res_lo, r, relu, out_hi, out_lo, \
+                            out_f32, M, C);                                                                     \
+  } else
+  VB_BN_CASE(4, 1) VB_BN_CASE(4, 2) VB_BN_CASE(4, 4) VB_BN_CASE(8, 1) VB_BN_CASE(8, 2) VB_BN_CASE(8, 4) {
+    VB_REQUIRE(false, "bn_apply: unsupported tuning %d", cfg);
+  }
+#undef VB_BN_CASE
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
 // stem: bn + relu + maxpool 3x3 stride 2 pad 1 (NHWC); padding behaves as -inf (torch max_pool2d).
-// One block per (image, output row, tile of MP_TQ output columns): the 3 x (2*MP_TQ+1) input pixels are normalised
-// once while being staged in shared memory (coalesced 16-byte loads), then reduced.
+// A thread owns (4 channels, one output column) and walks down a segment of output rows keeping the horizontal
+// max of the last input row in registers, so every input row is fetched once per segment (+1 row of overlap) and
+// the six 16-byte loads of an output row are issued back to back.  Neighbouring columns share one input column
+// through L1.  Block = C/4 channel groups x MP_TQ output columns; grid = (column tiles, row segments, images).
 // ------------------------------------------------------------------------------------------------
-constexpr int MP_TQ = 14;
-__global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(BnSideDev bn, __nv_bfloat16* __restrict__ out_hi,
-                                                              __nv_bfloat16* __restrict__ out_lo, int N, int P, int Q,
-                                                              int C, int P2, int Q2) {
-  extern __shared__ float4 tile4[];                   // [3][2*MP_TQ+1][C/4]
+constexpr int MP_ROWS = 14;                           // output rows per segment
+__device__ __forceinline__ float4 mp_hmax(const float* __restrict__ rowp, int xc, int Q, int C, const float4& sc,
+                                          const float4& sh) {
+  // max over input columns xc-1, xc, xc+1 of relu(bn(.)); rowp points at (row, col 0, this thread's channels)
+  const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  float4 l = ninf, m, r = ninf;
+  const float4* c4 = reinterpret_cast<const float4*>(rowp + (int64_t)xc * C);
+  m = __ldg(c4);
+  const bool hl = xc - 1 >= 0, hr = xc + 1 < Q;
+  if (hl) l = __ldg(reinterpret_cast<const float4*>(rowp + (int64_t)(xc - 1) * C));
+  if (hr) r = __ldg(reinterpret_cast<const float4*>(rowp + (int64_t)(xc + 1) * C));
+  m = relu4(fma4(m, sc, sh));
+  if (hl) m = max4(m, relu4(fma4(l, sc, sh)));
+  if (hr) m = max4(m, relu4(fma4(r, sc, sh)));
+  return m;
+}
+
+__global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(BnSideDev bn, __half* __restrict__ out_hi,
+                                                              __half* __restrict__ out_lo, int N, int P, int Q,
+                                                              int C, int P2, int Q2, int tq) {
   const int C4 = C >> 2;
-  const int q2_0 = blockIdx.x * MP_TQ;
-  const int p2 = blockIdx.y;
+  const int cg = threadIdx.x % C4;
+  const int q2 = blockIdx.x * tq + threadIdx.x / C4;
   const int n = blockIdx.z;
-  const int tid = threadIdx.x;
-  const int cols = 2 * MP_TQ + 1;
-  const int cg = tid % C4;
+  if (q2 >= Q2) return;
+  const int p2_0 = blockIdx.y * MP_ROWS;
+  const int p2_1 = min(p2_0 + MP_ROWS, P2);
   float4 sc, sh;
   bn_coeffs4(bn, cg * 4, C, sc, sh);
   const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-  // blockDim (256) is a multiple of C4, so a thread always serves the same channel group
-  for (int i = tid; i < 3 * cols * C4; i += blockDim.x) {
-    const int pix = i / C4;
-    const int dy = pix / cols, dx = pix - dy * cols;
-    const int y = 2 * p2 - 1 + dy, xx = 2 * q2_0 - 1 + dx;
-    float4 v = ninf;
-    if (y >= 0 && y < P && xx >= 0 && xx < Q)
-      v = relu4(fma4(__ldcs(reinterpret_cast<const float4*>(bn.raw + (((int64_t)n * P + y) * Q + xx) * C) + cg), sc, sh));
-    tile4[i] = v;
-  }
-  __syncthreads();
-  for (int i = tid; i < MP_TQ * C4; i += blockDim.x) {
-    const int t = i / C4;
-    const int q2 = q2_0 + t;
-    if (q2 >= Q2) break;
-    float4 m = ninf;
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) m = max4(m, tile4[(dy * cols + 2 * t + dx) * C4 + cg]);
-    bf16x4 h, l;
+  const int xc = 2 * q2;
+  const float* img = bn.raw + (int64_t)n * P * Q * C + cg * 4;
+  float4 prev = ninf;                                 // horizontal max of input row 2*p2 - 1
+  if (2 * p2_0 - 1 >= 0) prev = mp_hmax(img + (int64_t)(2 * p2_0 - 1) * Q * C, xc, Q, C, sc, sh);
+  for (int p2 = p2_0; p2 < p2_1; ++p2) {
+    const int y0 = 2 * p2, y1 = 2 * p2 + 1;
+    const float4 h0 = mp_hmax(img + (int64_t)y0 * Q * C, xc, Q, C, sc, sh);      // y0 <= P-1 always
+    float4 h1 = ninf;
+    if (y1 < P) h1 = mp_hmax(img + (int64_t)y1 * Q * C, xc, Q, C, sc, sh);
+    const float4 m = max4(max4(prev, h0), h1);
+    prev = h1;
+    h16x4 h, l;
     split4(m, h, l);
     const int64_t off = ((((int64_t)n * P2 + p2) * Q2) + q2) * C + cg * 4;
-    *reinterpret_cast<bf16x4*>(out_hi + off) = h;
-    if (out_lo) *reinterpret_cast<bf16x4*>(out_lo + off) = l;
+    *reinterpret_cast<h16x4*>(out_hi + off) = h;
+    if (out_lo) *reinterpret_cast<h16x4*>(out_lo + off) = l;
   }
 }
 
-int bn_relu_maxpool_launch(const BnSide& bn, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int N, int P, int Q, int C,
+int bn_relu_maxpool_launch(const BnSide& bn, __half* out_hi, __half* out_lo, int N, int P, int Q, int C,
                            int P2, int Q2, cudaStream_t stream) {
-  VB_REQUIRE(C % 4 == 0 && C <= 256 && 256 % (C / 4) == 0, "bn_relu_maxpool: unsupported channel count %d", C);
-  VB_REQUIRE(N <= 65535 && P2 <= 65535, "bn_relu_maxpool: shape too large");
+  VB_REQUIRE(C % 4 == 0 && C <= 1024, "bn_relu_maxpool: unsupported channel count %d", C);
+  VB_REQUIRE(N <= 65535 && P2 <= 65535 * MP_ROWS, "bn_relu_maxpool: shape too large");
   if ((int64_t)N * P2 * Q2 == 0) return VB_OK;
-  const size_t smem = (size_t)3 * (2 * MP_TQ + 1) * (C / 4) * sizeof(float4);
-  VB_REQUIRE(smem <= 48 * 1024, "bn_relu_maxpool: channel count %d too large", C);
-  dim3 grid((Q2 + MP_TQ - 1) / MP_TQ, P2, N);
-  bn_relu_maxpool_kernel<<<grid, 256, smem, stream>>>(to_dev(bn), out_hi, out_lo, N, P, Q, C, P2, Q2);
+  const int C4 = C / 4;
+  // output columns per block: the divisor-friendly choice with the fewest idle threads
+  int max_tq = 256 / C4;
+  if (max_tq < 1) max_tq = 1;
+  int tq = max_tq, best_waste = 1 << 30;
+  for (int t = max_tq; t >= (max_tq + 1) / 2; --t) {
+    const int tiles = (Q2 + t - 1) / t;
+    const int waste = tiles * t - Q2;
+    if (waste < best_waste) best_waste = waste, tq = t;
+  }
+  dim3 grid((Q2 + tq - 1) / tq, (P2 + MP_ROWS - 1) / MP_ROWS, N);
+  bn_relu_maxpool_kernel<<<grid, tq * C4, 0, stream>>>(to_dev(bn), out_hi, out_lo, N, P, Q, C, P2, Q2, tq);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }
@@ -304,8 +387,8 @@ int bn_relu_maxpool_launch(const BnSide& bn, __nv_bfloat16* out_hi, __nv_bfloat1
 // block = (image n, 32-channel slab); smem transpose so both the NHWC read and the NCHW write are coalesced
 // ------------------------------------------------------------------------------------------------
 constexpr int FP_CH = 32;
-__global__ void bn_final_pool_kernel(BnSideDev main, int res_kind, const __nv_bfloat16* __restrict__ res_hi,
-                                     const __nv_bfloat16* __restrict__ res_lo, BnSideDev res_bn,
+__global__ void bn_final_pool_kernel(BnSideDev main, int res_kind, const __half* __restrict__ res_hi,
+                                     const __half* __restrict__ res_lo, BnSideDev res_bn,
                                      const int64_t* __restrict__ scatter_idx, float* __restrict__ spatial,
                                      float* __restrict__ pooled, int N, int HW, int C) {
   extern __shared__ float tile[];                 // [FP_CH][HW + 1]
@@ -322,10 +405,10 @@ __global__ void bn_final_pool_kernel(BnSideDev main, int res_kind, const __nv_bf
     const int64_t off = ((int64_t)n * HW + pix) * C + c;
     float4 v = fma4(*reinterpret_cast<const float4*>(main.raw + off), sc, sh);
     if (res_kind == 1) {
-      const bf16x4 h = *reinterpret_cast<const bf16x4*>(res_hi + off);
-      bf16x4 l;
-      if (res_lo) l = *reinterpret_cast<const bf16x4*>(res_lo + off);
-      else l.v[0] = l.v[1] = l.v[2] = l.v[3] = __float2bfloat16_rn(0.f);
+      const h16x4 h = *reinterpret_cast<const h16x4*>(res_hi + off);
+      h16x4 l;
+      if (res_lo) l = *reinterpret_cast<const h16x4*>(res_lo + off);
+      else l.v[0] = l.v[1] = l.v[2] = l.v[3] = __float2half_rn(0.f);
       v = add4(v, join4(h, l));
     } else if (res_kind == 2) {
       v = add4(v, fma4(*reinterpret_cast<const float4*>(res_bn.raw + off), rsc, rsh));
@@ -353,7 +436,7 @@ __global__ void bn_final_pool_kernel(BnSideDev main, int res_kind, const __nv_bf
   }
 }
 
-int bn_final_pool_launch(const BnSide& main, int res_kind, const __nv_bfloat16* res_hi, const __nv_bfloat16* res_lo,
+int bn_final_pool_launch(const BnSide& main, int res_kind, const __half* res_hi, const __half* res_lo,
                          const BnSide& res_bn, const int64_t* scatter_idx, float* spatial_nchw, float* pooled, int N,
                          int HW, int C, cudaStream_t stream) {
   VB_REQUIRE(C % FP_CH == 0, "bn_final_pool: C=%d must be a multiple of %d", C, FP_CH);
@@ -372,20 +455,20 @@ int bn_final_pool_launch(const BnSide& main, int res_kind, const __nv_bfloat16* 
 // ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
-__global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
-                                  __nv_bfloat16* __restrict__ lo, int64_t n) {
+__global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi,
+                                  __half* __restrict__ lo, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    __nv_bfloat16 h, l;
-    split_bf16(x[i], h, l);
+    __half h, l;
+    split_f16(x[i], h, l);
     hi[i] = h;
     if (lo) lo[i] = l;
   }
 }
-int split_bf16_launch(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t stream) {
+int split_f16_launch(const float* x, __half* hi, __half* lo, int64_t n, cudaStream_t stream) {
   if (n == 0) return VB_OK;
   int blocks = div_up(n, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  split_bf16_kernel<<<blocks, 256, 0, stream>>>(x, hi, lo, n);
+  split_f16_kernel<<<blocks, 256, 0, stream>>>(x, hi, lo, n);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }

@@ -113,7 +113,8 @@ int encode_tma_4d_nhwc(CUtensorMap* map, CUtensorMapDataType dtype, const void* 
 // (q*stride - pad_lo_w, p*stride - pad_lo_h, n) and the filter tap is passed as the {s, r} offsets.
 int encode_tma_im2col_nhwc(CUtensorMap* map, CUtensorMapDataType dtype, const void* base, int N, int H, int W, int C,
                            int pad_lo_h, int pad_lo_w, int pad_hi_h, int pad_hi_w, int R, int S, int stride,
-                           uint32_t channels_per_pixel, uint32_t pixels_per_column, CUtensorMapSwizzle swz) {
+                           uint32_t channels_per_pixel, uint32_t pixels_per_column, CUtensorMapSwizzle swz,
+                           long long pixel_stride, long long row_stride, long long img_stride) {
   int rc = resolve();
   if (rc) return rc;
   const size_t eb = dtype_bytes(dtype);
@@ -121,7 +122,13 @@ int encode_tma_im2col_nhwc(CUtensorMap* map, CUtensorMapDataType dtype, const vo
   VB_REQUIRE(((size_t)C * eb) % 16 == 0, "TMA im2col: C*elem must be a multiple of 16 bytes (C=%d)", C);
   VB_REQUIRE(pixels_per_column <= 1024 && channels_per_pixel <= 256, "TMA im2col: box too large");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * eb, (cuuint64_t)W * C * eb, (cuuint64_t)H * W * C * eb};
+  // element strides between pixels / rows / images; a pixel stride below C gives overlapping pixel windows
+  const cuuint64_t ps = pixel_stride > 0 ? (cuuint64_t)pixel_stride : (cuuint64_t)C;
+  const cuuint64_t rs = row_stride > 0 ? (cuuint64_t)row_stride : (cuuint64_t)W * ps;
+  const cuuint64_t is = img_stride > 0 ? (cuuint64_t)img_stride : (cuuint64_t)H * rs;
+  VB_REQUIRE((ps * eb) % 16 == 0 && (rs * eb) % 16 == 0 && (is * eb) % 16 == 0,
+             "TMA im2col: strides must be multiples of 16 bytes");
+  cuuint64_t strides[3] = {ps * eb, rs * eb, is * eb};
   int lower[2] = {-pad_lo_w, -pad_lo_h};
   int upper[2] = {pad_hi_w - (S - 1), pad_hi_h - (R - 1)};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
@@ -137,7 +144,7 @@ int encode_tma_im2col_nhwc(CUtensorMap* map, CUtensorMapDataType dtype, const vo
   // drivers <= 13.1 set a descriptor bit that makes im2col loads fault; clear it.
   int drv = 0;
   if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010) {
-    const size_t bytes = (size_t)N * H * W * C * eb;
+    const size_t bytes = (size_t)N * is * eb;
     if (bytes < 131072) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
   }
   return VB_OK;

@@ -1,6 +1,6 @@
 // Internal C++ launch API of libvince_b200 (the exported C ABI in include/vince_b200.h wraps these 1:1).
 #pragma once
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
@@ -9,19 +9,20 @@ namespace vb {
 
 // ---- conv_gemm.cu -------------------------------------------------------------------------------
 struct ConvGemmDesc {
-  const void* a_hi;      // bf16 plane(s) of A: [M,K] row-major, or NHWC [batch,H,W,Cin] when im2col
+  const void* a_hi;      // fp16 plane(s) of A: [M,K] row-major, or NHWC [batch,H,W,Cin] when im2col
   const void* a_lo;
-  const void* b_hi;      // bf16 plane(s) of the weights, [N, K] row-major, K ordered (r, s, cin)
+  const void* b_hi;      // fp16 plane(s) of the weights, [N, K] row-major, K ordered (r, s, cin)
   const void* b_lo;
   float* out;            // fp32 [M, N]
   int M, N, K;
   int im2col;
   int batch, H, W, Cin, R, S, stride, pad_lo_h, pad_lo_w, pad_hi_h, pad_hi_w;
-  int passes;            // 3 = bf16x3 (fp32-grade), 1 = plain bf16
+  int passes;            // 3 = fp16x3 (fp32-grade), 1 = plain fp16
   int block_n;           // 0 = auto
   const float* scale;    // optional [N]
   const float* bias;     // optional [N]
   int relu;
+  float alpha;           // out = epilogue(alpha * A*W^T); 0 means 1 (used to undo the power-of-two weight pre-scale)
   double* stats;         // optional [2][N] (+=): per-channel sum and sum of squares of the raw outputs
   int halo_mode;         // 3x3 stride-1 convs: -1 auto (use the shared-memory halo path when efficient), 0 off, 1 force
   // optional train-mode BatchNorm finalize fused into the kernel tail (needs stats): the last CTA writes
@@ -34,6 +35,7 @@ struct ConvGemmDesc {
   float* bn_coef;
   unsigned int* bn_counter;   // must be 0 at launch
   float bn_momentum, bn_eps;
+  long long a_pixel_stride, a_row_stride, a_img_stride;   // im2col: element strides (0 = dense NHWC)
   void* trace;                // debug builds (-DVB_TRACE) only: [4][512] uint64 timeline of CTA 0
 };
 int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream);
@@ -42,38 +44,39 @@ int bn_eval_coef_launch(const float* gamma, const float* beta, const float* rm, 
                         int C, cudaStream_t stream);
 
 // ---- elementwise.cu -----------------------------------------------------------------------------
-// Stem input packing: NCHW fp32 image -> X[n, j, q, 64] bf16 hi/lo with
-//   X[n,j,q, r2*21 + s*3 + c] = x[idx[n], c, 2j-1+r2, 2q-3+s]   (0 outside the image, 0 for e >= 42)
-// so that the 7x7/2 pad-3 stem conv becomes a 4x1 stride-1 im2col conv over j with 64 "channels".
-int stem_pack_launch(const float* x, const int64_t* gather_idx, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int H,
-                     int W, int Hj, int Q, cudaStream_t stream);
+// Stem input packing: NCHW fp32 image -> X[n, a, b, 16] fp16 hi/lo (overlapping-window layout) with
+//   X[n,a,b,(dr*2+dc)*3 + c] = x[idx[n], c, 2(a-2)+dr, 2(b-2)+dc]   (0 outside the image, 0 for e >= 12)
+// so that the 7x7/2 pad-3 stem conv becomes a 4x1 stride-1 im2col conv over row pairs with 64-element pixels read
+// at a pixel stride of 16 elements.
+int stem_pack_launch(const float* x, const int64_t* gather_idx, __half* hi, __half* lo, int N, int H,
+                     int W, int Ha, int Wb, cudaStream_t stream);
 
 struct WeightPrepEntry {   // one per weight tensor; lives in device memory
   const float* src;        // OIHW fp32 (Linear: [Cout, Cin] with R=S=1)
   int64_t dst_off;         // element offset into the hi / lo planes
   int32_t Cout, Cin, R, S;
-  int32_t kind;            // 0: [Cout][R][S][Cin]; 1: stem packing [64][4][64]
-  int32_t pad;
+  int32_t kind;            // 0: [Cout][R][S][Cin]; 1: stem packing [64][4][4][16]
+  int32_t scale_log2;      // weights are multiplied by 2^scale_log2 before the fp16 split (keeps lo planes normal)
 };
-int weight_prep_launch(const WeightPrepEntry* table_dev, int n_entries, int64_t max_elems, __nv_bfloat16* hi,
-                       __nv_bfloat16* lo, cudaStream_t stream);
+int weight_prep_launch(const WeightPrepEntry* table_dev, int n_entries, int64_t max_elems, __half* hi,
+                       __half* lo, cudaStream_t stream);
 
 struct BnSide {
   const float* raw;        // [M, C] raw conv output
   const float* coef;       // [2][C] per-channel (scale, shift) written by conv_gemm's fused finalize / bn_eval_coef
 };
 // out = relu?( bn(main) + residual ), residual = none | hi+lo planes | bn(second raw tensor)
-int bn_apply_launch(const BnSide& main, int res_kind, const __nv_bfloat16* res_hi, const __nv_bfloat16* res_lo,
-                    const BnSide& res_bn, int relu, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, float* out_f32,
+int bn_apply_launch(const BnSide& main, int res_kind, const __half* res_hi, const __half* res_lo,
+                    const BnSide& res_bn, int relu, __half* out_hi, __half* out_lo, float* out_f32,
                     int64_t M, int C, cudaStream_t stream);
 // stem: bn + relu + 3x3/2 pad-1 max pool, NHWC
-int bn_relu_maxpool_launch(const BnSide& bn, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int N, int P, int Q, int C,
+int bn_relu_maxpool_launch(const BnSide& bn, __half* out_hi, __half* out_lo, int N, int P, int Q, int C,
                            int P2, int Q2, cudaStream_t stream);
 // last block: relu(bn(main)+residual) -> NCHW fp32 spatial features (rows scattered by scatter_idx) + global mean
-int bn_final_pool_launch(const BnSide& main, int res_kind, const __nv_bfloat16* res_hi, const __nv_bfloat16* res_lo,
+int bn_final_pool_launch(const BnSide& main, int res_kind, const __half* res_hi, const __half* res_lo,
                          const BnSide& res_bn, const int64_t* scatter_idx, float* spatial_nchw, float* pooled, int N,
                          int HW, int C, cudaStream_t stream);
-int split_bf16_launch(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t stream);
+int split_f16_launch(const float* x, __half* hi, __half* lo, int64_t n, cudaStream_t stream);
 int l2_normalize_launch(const float* x, float* out, int rows, int D, float eps, cudaStream_t stream);
 // NCHW fp32 [N,C,H,W] -> jigsaw patches NCHW [9N,C,H3,W3] (pad bottom/right with zeros to a multiple of 3)
 int jigsaw_patchify_launch(const float* x, const int64_t* gather_idx, float* out, int N, int C, int H, int W, int H3,

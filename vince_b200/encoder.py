@@ -1,7 +1,7 @@
 """Host-side execution plan of the ResNet encoder forward on sm_100a kernels.
 
 `EncoderRunner` walks a torchvision-shaped ResNet parameter tree once, records one `ConvSpec` per convolution
-(where its prepared bf16 weights live, which BatchNorm follows it) and, per input shape, builds a PLAN: a list of
+(where its prepared fp16 weights live, which BatchNorm follows it) and, per input shape, builds a PLAN: a list of
 pre-marshalled kernel launches over a statically allocated activation arena (buffers are reused as soon as their
 last consumer has been issued).  Replaying a plan costs one ctypes call per kernel:
 
@@ -10,7 +10,7 @@ last consumer has been issued).  Replaying a plan costs one ctypes call per kern
     -> last block: bn_final_pool (relu(bn+residual) -> NCHW spatial features + global average pool)
 
 Reference arithmetic being reproduced: models/building_blocks/resnet.py:76-92 (BasicBlock), :117-137 (Bottleneck),
-:231-247 (stem + layers) as reached through backbone_models.py:39-54.  Activations live in HBM as NHWC bf16
+:231-247 (stem + layers) as reached through backbone_models.py:39-54.  Activations live in HBM as NHWC fp16
 (hi, lo) pairs; raw conv outputs as NHWC fp32 (see DESIGN.md "data layout").
 """
 import numpy as np
@@ -19,7 +19,12 @@ import torch
 from . import ops
 
 _WEIGHT_ENTRY = np.dtype([("src", "<u8"), ("dst_off", "<i8"), ("Cout", "<i4"), ("Cin", "<i4"), ("R", "<i4"),
-                          ("S", "<i4"), ("kind", "<i4"), ("pad", "<i4")])
+                          ("S", "<i4"), ("kind", "<i4"), ("scale_log2", "<i4")])
+
+# Weights are multiplied by 2^WEIGHT_SCALE_LOG2 (exact) before the fp16 hi/lo split so that the lo plane of O(1e-2)
+# weights is a normal fp16 number; the conv kernel multiplies its accumulators by 2^-WEIGHT_SCALE_LOG2 (exact).
+WEIGHT_SCALE_LOG2 = 6
+WEIGHT_ALPHA = 2.0 ** -WEIGHT_SCALE_LOG2
 
 
 def _align(n, a):
@@ -41,7 +46,7 @@ class ConvSpec:
 
 
 class WeightBank:
-    """bf16 (hi, lo) K-major copies of a set of conv / linear weights, refreshed by ONE multi-tensor launch."""
+    """fp16 (hi, lo) K-major copies of a set of conv / linear weights, refreshed by ONE multi-tensor launch."""
 
     def __init__(self, specs, passes):
         self.specs = specs
@@ -74,10 +79,10 @@ class WeightBank:
                 raise TypeError("vince_b200: weights must be contiguous fp32")
             R = s.R
             arr[i] = (s.weight.data_ptr(), s.w_off, s.Cout, 3 if s.kind == 1 else s.Cin, 7 if s.kind == 1 else R,
-                      7 if s.kind == 1 else R, s.kind, 0)
+                      7 if s.kind == 1 else R, s.kind, WEIGHT_SCALE_LOG2)
         self.table = torch.from_numpy(arr.view(np.uint8).copy()).to(dev)
-        self.w_hi = torch.empty((self.total,), device=dev, dtype=torch.bfloat16)
-        self.w_lo = torch.empty((self.total,), device=dev, dtype=torch.bfloat16) if self.passes == 3 else None
+        self.w_hi = torch.empty((self.total,), device=dev, dtype=torch.float16)
+        self.w_lo = torch.empty((self.total,), device=dev, dtype=torch.float16) if self.passes == 3 else None
         self._run = ops.build_weight_prep(self.table, len(self.specs), self.max_elems, self.w_hi, self.w_lo)
         self._ptrs, self.device = ptrs, dev
         self.generation += 1
@@ -128,7 +133,7 @@ class _Arena:
 
 
 class Act:
-    """NHWC activation as bf16 planes."""
+    """NHWC activation as fp16 planes."""
     __slots__ = ("hi", "lo", "N", "H", "W", "C")
 
     def __init__(self, hi, lo, N, H, W, C):
@@ -143,7 +148,7 @@ class _Plan:
 class EncoderRunner:
     def __init__(self, model, passes=3):
         if passes not in (1, 3):
-            raise ValueError("passes must be 3 (bf16x3, fp32-grade) or 1 (plain bf16)")
+            raise ValueError("passes must be 3 (fp16x3, fp32-grade) or 1 (plain fp16)")
         self.passes = passes
         self.model = model
         self.stem = ConvSpec(model.conv1.weight, model.bn1, 2, 3, kind=1)
@@ -211,12 +216,13 @@ class EncoderRunner:
                         pad_lo_h=spec.pad, pad_lo_w=spec.pad, pad_hi_h=spec.pad, pad_hi_w=spec.pad)
         launches.append(ops.build_conv_fwd(act.hi, act.lo, w_hi, w_lo, raw, M, spec.Cout, spec.K, passes=self.passes,
                                            geom=geom, block_n=self._block_n(M, spec.Cout), halo_mode=self.halo_mode,
+                                           alpha=WEIGHT_ALPHA,
                                            **self._bn_args(spec, work, train)))
         return raw, P, Q
 
     def _planes(self, arena, M, C):
-        hi = arena.alloc((M, C), torch.bfloat16)
-        lo = arena.alloc((M, C), torch.bfloat16) if self.passes == 3 else None
+        hi = arena.alloc((M, C), torch.float16)
+        lo = arena.alloc((M, C), torch.float16) if self.passes == 3 else None
         return hi, lo
 
     def _side(self, raw, spec, work):
@@ -239,14 +245,15 @@ class EncoderRunner:
         plan.idx_scatter = torch.zeros((N,), device=dev, dtype=torch.int64)
         # ---- stem (stem_pack itself is bound per call: it reads the caller's tensor) ----
         sg = ops.stem_geometry(H, W)
-        P, Q, Hj = sg["P"], sg["Q"], sg["Hj"]
-        plan.x_hi = arena.alloc((N, Hj, Q, 64), torch.bfloat16)
-        plan.x_lo = arena.alloc((N, Hj, Q, 64), torch.bfloat16) if self.passes == 3 else None
+        P, Q = sg["P"], sg["Q"]
+        plan.x_hi = arena.alloc((N, sg["Ha"], sg["Wb"], 16), torch.float16)
+        plan.x_lo = arena.alloc((N, sg["Ha"], sg["Wb"], 16), torch.float16) if self.passes == 3 else None
         w_hi, w_lo = self.bank.planes(self.stem)
         M = N * P * Q
         raw = arena.alloc((M, 64), torch.float32)
         launches.append(ops.build_conv_fwd(plan.x_hi, plan.x_lo, w_hi, w_lo, raw, M, 64, 256, passes=self.passes,
-                                           geom=dict(sg["geom"], batch=N), **self._bn_args(self.stem, work, train)))
+                                           geom=dict(sg["geom"], batch=N), alpha=WEIGHT_ALPHA,
+                                           **self._bn_args(self.stem, work, train)))
         arena.free(plan.x_hi, plan.x_lo)
         P2, Q2 = (P - 1) // 2 + 1, (Q - 1) // 2 + 1
         hi, lo = self._planes(arena, N * P2 * Q2, 64)
@@ -356,11 +363,12 @@ class HeadRunner:
         spec = self.specs[idx]
         M = x.shape[0]
         dev = x.device
-        hi = torch.empty((M, spec.Cin), device=dev, dtype=torch.bfloat16)
+        hi = torch.empty((M, spec.Cin), device=dev, dtype=torch.float16)
         lo = torch.empty_like(hi) if self.passes == 3 else None
-        ops.split_bf16(x.contiguous(), hi, lo)
+        ops.split_f16(x.contiguous(), hi, lo)
         out = torch.empty((M, spec.Cout), device=dev, dtype=torch.float32)
         w_hi, w_lo = self.bank.planes(spec)
-        ops.conv_fwd(hi, lo, w_hi, w_lo, out, M, spec.Cout, spec.K, passes=self.passes, bias=spec.bias, relu=relu)
+        ops.conv_fwd(hi, lo, w_hi, w_lo, out, M, spec.Cout, spec.K, passes=self.passes, bias=spec.bias, relu=relu,
+                     alpha=WEIGHT_ALPHA)
         self.launches += 2
         return out

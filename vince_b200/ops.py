@@ -70,14 +70,14 @@ def build_bn_eval_coef(bn, coef):
 
 # ---------------------------------------------------------------------------------------------------------------
 def build_conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, block_n=0, scale=None, bias=None,
-                   relu=False, stats=None, bn=None, coef=None, counter=None, halo_mode=-1):
+                   relu=False, stats=None, bn=None, coef=None, counter=None, halo_mode=-1, alpha=1.0):
     """geom=None: A is [M,K]; else dict(batch,H,W,Cin,R,S,stride,pad_lo_h,pad_lo_w,pad_hi_h,pad_hi_w) (NHWC gather).
     bn/coef/counter (with stats): fuse the train-mode BatchNorm finalize of module `bn` into the kernel tail."""
     d = _lib.ConvDesc()
-    d.a_hi = _val(a_hi, torch.bfloat16, "a_hi")
-    d.a_lo = _val(a_lo, torch.bfloat16, "a_lo")
-    d.w_hi = _val(w_hi, torch.bfloat16, "w_hi")
-    d.w_lo = _val(w_lo, torch.bfloat16, "w_lo")
+    d.a_hi = _val(a_hi, torch.float16, "a_hi")
+    d.a_lo = _val(a_lo, torch.float16, "a_lo")
+    d.w_hi = _val(w_hi, torch.float16, "w_hi")
+    d.w_lo = _val(w_lo, torch.float16, "w_lo")
     d.out = _val(out, torch.float32, "out")
     if out.numel() < M * N:
         raise ValueError("conv_fwd: output buffer too small")
@@ -86,6 +86,8 @@ def build_conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, bl
         d.im2col = 1
         for k in ("batch", "H", "W", "Cin", "R", "S", "stride", "pad_lo_h", "pad_lo_w", "pad_hi_h", "pad_hi_w"):
             setattr(d, k, int(geom[k]))
+        for k in ("a_pixel_stride", "a_row_stride", "a_img_stride"):       # 0 = dense NHWC
+            setattr(d, k, int(geom.get(k, 0)))
     d.passes = passes
     d.block_n = block_n
     d.scale = _val(scale, torch.float32, "scale")
@@ -93,6 +95,7 @@ def build_conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, bl
     d.relu = 1 if relu else 0
     d.stats = _val(stats, torch.float64, "stats")
     d.halo_mode = halo_mode
+    d.alpha = float(alpha)
     if bn is not None:
         if stats is None or coef is None or counter is None:
             raise ValueError("conv_fwd: the fused BatchNorm finalize needs stats, coef and counter buffers")
@@ -131,10 +134,11 @@ def conv_fwd(*a, **k):
 def stem_geometry(H, W):
     """Shapes of the packed stem input and the equivalent 4x1 conv (see include/vince_b200.h: vince_stem_pack)."""
     P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-    Hj = H // 2 + 1
-    return dict(P=P, Q=Q, Hj=Hj,
-                geom=dict(H=Hj, W=Q, Cin=64, R=4, S=1, stride=1, pad_lo_h=1, pad_lo_w=0, pad_hi_h=P + 2 - Hj,
-                          pad_hi_w=0, K_true=147))      # algorithmic K of the 7x7x3 stem (the packed K is 256)
+    Ha, Wb = P + 3, Q + 3                               # row pairs / column pairs stored (16 elements each)
+    return dict(P=P, Q=Q, Ha=Ha, Wb=Wb,
+                geom=dict(H=Ha, W=Q, Cin=64, R=4, S=1, stride=1, pad_lo_h=0, pad_lo_w=0, pad_hi_h=0, pad_hi_w=0,
+                          a_pixel_stride=16, a_row_stride=16 * Wb, a_img_stride=16 * Wb * Ha,
+                          K_true=147))                  # algorithmic K of the 7x7x3 stem (the packed K is 256)
 
 
 def build_stem_pack(x, gather_idx, x_hi, x_lo):
@@ -142,8 +146,8 @@ def build_stem_pack(x, gather_idx, x_hi, x_lo):
     if C != 3:
         raise ValueError("stem_pack: expected 3 input channels")
     run = _bind(_lib.lib().vince_stem_pack, "vince_stem_pack", _ptr(x, torch.float32, "x"),
-                _ptr(gather_idx, torch.int64, "gather_idx"), _ptr(x_hi, torch.bfloat16, "x_hi"),
-                _ptr(x_lo, torch.bfloat16, "x_lo"), N, H, W)
+                _ptr(gather_idx, torch.int64, "gather_idx"), _ptr(x_hi, torch.float16, "x_hi"),
+                _ptr(x_lo, torch.float16, "x_lo"), N, H, W)
     run._keep = (x, gather_idx, x_hi, x_lo)
     return run
 
@@ -154,7 +158,7 @@ def stem_pack(*a):
 
 def build_weight_prep(table_dev, n_entries, max_elems, w_hi, w_lo):
     run = _bind(_lib.lib().vince_weight_prep, "vince_weight_prep", _ptr(table_dev, torch.uint8, "table"), n_entries,
-                max_elems, _ptr(w_hi, torch.bfloat16, "w_hi"), _ptr(w_lo, torch.bfloat16, "w_lo"))
+                max_elems, _ptr(w_hi, torch.float16, "w_hi"), _ptr(w_lo, torch.float16, "w_lo"))
     run._keep = (table_dev, w_hi, w_lo)
     return run
 
@@ -165,7 +169,7 @@ def weight_prep(*a):
 
 def _residual(res_planes, res_bn):
     if res_planes is not None:
-        return 1, _ptr(res_planes[0], torch.bfloat16, "res_hi"), _ptr(res_planes[1], torch.bfloat16, "res_lo"), None
+        return 1, _ptr(res_planes[0], torch.float16, "res_hi"), _ptr(res_planes[1], torch.float16, "res_lo"), None
     if res_bn is not None:
         return 2, None, None, ctypes.byref(res_bn)
     return 0, None, None, None
@@ -174,7 +178,7 @@ def _residual(res_planes, res_bn):
 def build_bn_apply(main, M, C, relu, out_hi=None, out_lo=None, out_f32=None, res_planes=None, res_bn=None):
     res_kind, rh, rl, rb = _residual(res_planes, res_bn)
     run = _bind(_lib.lib().vince_bn_apply, "vince_bn_apply", ctypes.byref(main), res_kind, rh, rl, rb,
-                1 if relu else 0, _ptr(out_hi, torch.bfloat16, "out_hi"), _ptr(out_lo, torch.bfloat16, "out_lo"),
+                1 if relu else 0, _ptr(out_hi, torch.float16, "out_hi"), _ptr(out_lo, torch.float16, "out_lo"),
                 _ptr(out_f32, torch.float32, "out_f32"), M, C)
     run._keep = (main, res_planes, res_bn, out_hi, out_lo, out_f32)
     return run
@@ -186,7 +190,7 @@ def bn_apply(*a, **k):
 
 def build_bn_relu_maxpool(bn, out_hi, out_lo, N, P, Q, C):
     run = _bind(_lib.lib().vince_bn_relu_maxpool, "vince_bn_relu_maxpool", ctypes.byref(bn),
-                _ptr(out_hi, torch.bfloat16, "out_hi"), _ptr(out_lo, torch.bfloat16, "out_lo"), N, P, Q, C)
+                _ptr(out_hi, torch.float16, "out_hi"), _ptr(out_lo, torch.float16, "out_lo"), N, P, Q, C)
     run._keep = (bn, out_hi, out_lo)
     return run
 
@@ -208,15 +212,15 @@ def bn_final_pool(*a, **k):
     build_bn_final_pool(*a, **k)()
 
 
-def build_split_bf16(x, hi, lo):
-    run = _bind(_lib.lib().vince_split_bf16, "vince_split_bf16", _ptr(x, torch.float32, "x"),
-                _ptr(hi, torch.bfloat16, "hi"), _ptr(lo, torch.bfloat16, "lo"), x.numel())
+def build_split_f16(x, hi, lo):
+    run = _bind(_lib.lib().vince_split_f16, "vince_split_f16", _ptr(x, torch.float32, "x"),
+                _ptr(hi, torch.float16, "hi"), _ptr(lo, torch.float16, "lo"), x.numel())
     run._keep = (x, hi, lo)
     return run
 
 
-def split_bf16(*a):
-    build_split_bf16(*a)()
+def split_f16(*a):
+    build_split_f16(*a)()
 
 
 def round_tf32(x, out):

@@ -102,9 +102,9 @@ class LazySimilarity:
                         xp = torch.zeros((x.shape[0], Dp), device=dev, dtype=torch.float32)
                         xp[:, :D] = x
                         x = xp
-                    hi = torch.empty(x.shape, device=dev, dtype=torch.bfloat16)
+                    hi = torch.empty(x.shape, device=dev, dtype=torch.float16)
                     lo = torch.empty_like(hi)
-                    ops.split_bf16(x.contiguous(), hi, lo)
+                    ops.split_f16(x.contiguous(), hi, lo)
                     return hi, lo
                 q_hi, q_lo = planes(self.q)
                 outs = []
@@ -113,7 +113,7 @@ class LazySimilarity:
                     n_pad = (n + 31) // 32 * 32
                     c_hi, c_lo = planes(cols)
                     if n_pad != n:
-                        pad = torch.zeros((n_pad - n, Dp), device=dev, dtype=torch.bfloat16)
+                        pad = torch.zeros((n_pad - n, Dp), device=dev, dtype=torch.float16)
                         c_hi, c_lo = torch.cat((c_hi, pad)), torch.cat((c_lo, pad))
                     out = torch.empty((B, n_pad), device=dev, dtype=torch.float32)
                     ops.conv_fwd(q_hi, q_lo, c_hi, c_lo, out, B, n_pad, Dp, passes=3)
