@@ -105,7 +105,10 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 // 128 A rows and HALF of the weight tile, which halves both the MMA-dispatch load and the weight bytes per SM.
 // HALO selects the A-operand mode 2 code paths at compile time (the MMA-issuing thread is the critical resource:
 // its loop must carry no mode checks, divisions or 64-bit descriptor arithmetic).
-template <int BN, int CG, bool HALO>
+// RES ("resident weights"): the layer has a single n-block and this CTA's share of the whole [N, K] weight matrix
+// fits in shared memory next to the activation ring, so it is loaded ONCE per CTA; afterwards only activations
+// stream and the issuing thread waits on / commits to one barrier per activation stage instead of one per k-block.
+template <int BN, int CG, bool HALO, bool RES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B tiles
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
   const int tile_step = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t a_stage_bytes = p.a_plane_bytes * planes;
   const uint32_t b_stage_bytes = B_TILE * planes;
-  constexpr bool merged = !HALO;                   // A and B rings advance in lockstep and share barriers
+  constexpr bool merged = !HALO && !RES;           // A and B rings advance in lockstep and share barriers
 
   uint8_t* a_ring = smem;
   uint8_t* b_ring = a_ring + (size_t)p.a_stages * a_stage_bytes;
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       mbar_init(&a_full[s], (uint32_t)planes + fwd);
       mbar_init(&a_empty[s], 1);
     }
-    for (int s = 0; s < p.b_stages; ++s) {
+    for (int s = 0; s < (RES ? 1 : p.b_stages); ++s) {       // RES: one barrier for the one-time weight load
       mbar_init(&b_full[s], (uint32_t)planes * (merged ? 2u : 1u) + fwd);
       mbar_init(&b_empty[s], 1);
     }
@@ -250,6 +253,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       int bs = 0;
       uint32_t bphase = 0;
       int tr_p = 0;
+      if (RES) {
+        // whole weight share of this CTA, once: slot (ac * taps + bi) holds the k-block the MMA loop consumes then
+        if (tile_start < num_tiles) {
+          const int nrow = (int)cta_rank * (BN / CG);
+          const int total_kb = p.a_chunks * p.b_per_a;
+          if (elect_one()) {
+            mbar_expect_tx(&b_full[0], (uint32_t)total_kb * B_TILE);
+            for (int ac = 0; ac < p.a_chunks; ++ac)
+              for (int bi = 0; bi < p.b_per_a; ++bi) {
+                const int kb = HALO ? (bi * p.a_chunks + ac) : ac;
+                uint8_t* dst = b_ring + (size_t)(ac * p.b_per_a + bi) * b_stage_bytes + (size_t)plane * B_TILE;
+                tma_load_2d(dst, bmap, &b_full[0], kb * BK, nrow);
+              }
+          }
+          __syncwarp();
+        }
+      } else {
       for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
         const int n_blk = tile / p.num_m_blocks;
         // this CTA's share of the weight tile (all of it, or its half when paired)
@@ -277,6 +297,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
           }
         }
       }
+      }
     }
   } else if (warp == 4) {
     // ======================= MMA issuer (leader CTA only when CG == 2) =======================
@@ -287,13 +308,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     int tr_m = 0;
     if (CG == 2 && cta_rank == 1) {
       // peer CTA: forward "my operands have landed" to the leader's barriers, one remote arrive per stage use
+      if (RES && tile_start < num_tiles) {
+        mbar_wait(&b_full[0], 0);
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&b_full[0]), 0));
+      }
       for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
         for (int ac = 0; ac < p.a_chunks; ++ac) {
           if (!merged) {
             mbar_wait(&a_full[as], aphase);
             if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&a_full[as]), 0));
           }
-          for (int bi = 0; bi < p.b_per_a; ++bi) {
+          for (int bi = 0; bi < (RES ? 0 : p.b_per_a); ++bi) {
             mbar_wait(&b_full[bs], bphase);
             if (lane == 0) VB_TRACE_EVENT(5, tr_m);
             ++tr_m;
@@ -325,6 +350,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     const bool skip_mma = (p.debug_skip_mma & 1) != 0;
     const int a_chunks = p.a_chunks, a_stages = p.a_stages, b_stages = p.b_stages;
     const uint32_t wp8 = (uint32_t)p.Wp * 8u;            // halo: one padded image row in descriptor units
+    if (RES && cta_rank == 0 && tile_start < num_tiles) {
+      mbar_wait(&b_full[0], 0);                          // resident weights (both CTAs' shares) have landed
+      tc_fence_after_sync();
+    }
     for (int tile = (cta_rank == 0 ? tile_start : num_tiles); tile < num_tiles; tile += tile_step, ++local_t) {
       const int acc = local_t & 1;
       const uint32_t acc_phase = (local_t >> 1) & 1;
@@ -333,22 +362,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       const uint32_t d_tmem = tmem_base + acc * BN;
       uint32_t accumulate = 0;
       for (int ac = 0; ac < a_chunks; ++ac) {
-        uint32_t a_w;
-        if (HALO) {
+        uint32_t a_w = 0;
+        if (!merged) {
           mbar_wait_addr(a_full0 + 8u * as, aphase);
+          if (RES) tc_fence_after_sync();
           a_w = a_ring_w + (uint32_t)as * a_stage_w;
         }
         const bool last_chunk = (ac == a_chunks - 1);
         constexpr int TAPS = HALO ? 9 : 1;
 #pragma unroll
         for (int bi = 0; bi < TAPS; ++bi) {
-          mbar_wait_addr(b_full0 + 8u * bs, bphase);
-          tc_fence_after_sync();
+          if (!RES) {
+            mbar_wait_addr(b_full0 + 8u * bs, bphase);
+            tc_fence_after_sync();
+          }
           if (lane == 0) VB_TRACE_EVENT(1, tr_m);
           // halo mode: filter tap (r, s) = rows shifted by r*(W+2)+s inside the halo tile
           const uint32_t aw = HALO ? a_w + (uint32_t)(bi / 3) * wp8 + (uint32_t)(bi % 3) * 8u
-                                   : a_ring_w + (uint32_t)bs * a_stage_w;
-          const uint32_t bw = b_ring_w + (uint32_t)bs * b_stage_w;
+                                   : (merged ? a_ring_w + (uint32_t)bs * a_stage_w : a_w);
+          const uint32_t bw = b_ring_w + (uint32_t)(RES ? ac * TAPS + bi : bs) * b_stage_w;
           if (elect_one()) {
             if (!skip_mma) {
               if (planes == 2) {
@@ -369,19 +401,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
               }
             }
             const bool last_b = (bi == TAPS - 1);
-            umma_commit_addr<CG>(b_empty0 + 8u * bs);                 // frees the weight slot (in BOTH CTAs of a pair)
-            if (HALO && last_b) umma_commit_addr<CG>(a_empty0 + 8u * as);   // ... the halo slot after its last tap
+            if (!RES) umma_commit_addr<CG>(b_empty0 + 8u * bs);      // frees the weight slot (in BOTH CTAs of a pair)
+            if (!merged && last_b) umma_commit_addr<CG>(a_empty0 + 8u * as);   // ... the activation slot after its last tap
             if (last_b && last_chunk) umma_commit_addr<CG>(smem_u32(&tmem_full[acc]));   // accumulators ready
           }
           accumulate = 1;
           if (lane == 0) VB_TRACE_EVENT(2, tr_m);
           ++tr_m;
-          if (++bs == b_stages) {
-            bs = 0;
-            bphase ^= 1;
+          if (!RES) {
+            if (++bs == b_stages) {
+              bs = 0;
+              bphase ^= 1;
+            }
           }
         }
-        if (HALO) {
+        if (!merged) {
           if (++as == a_stages) {
             as = 0;
             aphase ^= 1;
@@ -618,16 +652,16 @@ static size_t fixed_smem(int bn) {
   return 1024 /*align slack*/ + STAGING_BYTES + (4 * MAX_RING + 4) * 8 + 16 + 8 * bn * 8;
 }
 
-template <int BN, int CG, bool HALO>
+template <int BN, int CG, bool HALO, bool RES>
 static int launch_gemm(const GemmKernelParams& kp, size_t smem, int grid, cudaStream_t stream) {
   static size_t smem_set = 0;                        // per instantiation: the opt-in only ever needs to grow
   if (smem > smem_set) {
-    VB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, CG, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, CG, HALO, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)SMEM_BUDGET));
     smem_set = SMEM_BUDGET;
   }
   if (CG == 1) {
-    conv_gemm_kernel<BN, CG, HALO><<<grid, GEMM_THREADS, smem, stream>>>(kp);
+    conv_gemm_kernel<BN, CG, HALO, RES><<<grid, GEMM_THREADS, smem, stream>>>(kp);
   } else {
     grid &= ~1;
     cudaLaunchConfig_t cfg;
@@ -643,7 +677,7 @@ static int launch_gemm(const GemmKernelParams& kp, size_t smem, int grid, cudaSt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CG, HALO>, kp));
+    VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CG, HALO, RES>, kp));
   }
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
@@ -823,7 +857,21 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   const size_t a_stage = (size_t)kp.a_plane_bytes * planes;
   const size_t b_stage = (size_t)(bn / cg) * 128 * planes;
   const size_t avail = SMEM_BUDGET - fixed_smem(bn);
-  if (kp.a_mode == 2) {
+  // resident weights: single n-block, this CTA's whole weight share + two activation stages fit, and every CTA
+  // works through several tiles (otherwise the ring version overlaps the weight load just as well)
+  const int total_kb = kp.a_chunks * kp.b_per_a;
+  const bool res_ok = kp.num_n_blocks == 1 && (size_t)total_kb * b_stage + 2 * a_stage <= avail;
+  bool res = res_ok && (kp.num_m_blocks + cg - 1) / cg >= 2 * (num_sms() / cg);
+  {
+    const char* e = getenv("VINCE_B200_RESIDENT");     // debug / A-B comparison: 0 disables, 2 forces when feasible
+    if (e && atoi(e) == 0) res = false;
+    if (e && atoi(e) == 2) res = res_ok;
+  }
+  if (res) {
+    kp.b_stages = total_kb;
+    int st = (int)((avail - (size_t)total_kb * b_stage) / a_stage);
+    kp.a_stages = st > MAX_RING ? MAX_RING : st;
+  } else if (kp.a_mode == 2) {
     kp.a_stages = 2;
     VB_REQUIRE(avail > 2 * a_stage + 2 * b_stage, "conv_gemm: halo tile does not fit in shared memory");
     int bs = (int)((avail - 2 * a_stage) / b_stage);
@@ -843,8 +891,12 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   const bool halo = kp.a_mode == 2;
   if (cg == 2) grid &= ~1;
 #define VB_LAUNCH(BN_, CG_)                                                              \
-  if (bn == BN_ && cg == CG_)                                                            \
-    return halo ? launch_gemm<BN_, CG_, true>(kp, smem, grid, stream) : launch_gemm<BN_, CG_, false>(kp, smem, grid, stream);
+  if (bn == BN_ && cg == CG_) {                                                          \
+    if (halo) return res ? launch_gemm<BN_, CG_, true, true>(kp, smem, grid, stream)     \
+                         : launch_gemm<BN_, CG_, true, false>(kp, smem, grid, stream);   \
+    return res ? launch_gemm<BN_, CG_, false, true>(kp, smem, grid, stream)              \
+               : launch_gemm<BN_, CG_, false, false>(kp, smem, grid, stream);            \
+  }
   VB_LAUNCH(64, 1) VB_LAUNCH(128, 1) VB_LAUNCH(256, 1) VB_LAUNCH(64, 2) VB_LAUNCH(128, 2) VB_LAUNCH(256, 2)
 #undef VB_LAUNCH
   VB_REQUIRE(false, "conv_gemm: no kernel for bn=%d cg=%d", bn, cg);
