@@ -158,6 +158,17 @@ typedef struct {
   void* workspace;
 } vince_infonce_desc;
 size_t vince_infonce_workspace_bytes(int32_t B, int32_t D);
+/* ---- fused InfoNCE backward w.r.t. the queries ---------------------------------------------------------------
+ * replaces: what autograd computes for `embeddings` through vince_model.py:213-233 + utils/loss_util.py:7-62 when
+ *           vince_solver.py:465 calls loss.backward() (keys and queue are detached: vince_model.py:598,610,
+ *           storage_queue.py:53).  dq[B,D] = d(grad_dist * dist)/dq.  `desc` is the forward's descriptor: q, keys,
+ *           queue_tf32, shapes and temperature as in the forward, pos_sim and row_lse as the forward WROTE them
+ *           (inputs here); dists / weights / neg_max / scalars are ignored; workspace >=
+ *           vince_infonce_bwd_workspace_bytes.  symmetric = 1: the self-batch loss (vince_model.py:213-222; keys ==
+ *           q, K == 0), whose columns carry gradient too.  accumulate = 1 adds to dq. */
+size_t vince_infonce_bwd_workspace_bytes(int32_t B, int32_t D);
+int vince_infonce_bwd(const vince_infonce_desc* desc, float grad_dist, int32_t symmetric, int32_t accumulate, float* dq,
+                      void* stream);
 int vince_infonce_fwd(const vince_infonce_desc* desc, void* stream);
 
 /* explicit-matrix form with the literal signature of loss_util.similarity_cross_entropy (utils/loss_util.py:7-62,

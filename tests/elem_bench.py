@@ -48,6 +48,28 @@ def main():
         bench_stem(a, dev, B, nbuf)
     if not a.only or a.only in "bn_apply":
         bench_bn_apply(a, dev, B, nbuf)
+    if not a.only or a.only in "nce":
+        bench_nce(a, dev, B)
+
+
+def bench_nce(a, dev, B):
+    """fused InfoNCE forward / backward at K=65536, D=128 (three queue copies cycled: 3 x 32 MiB > L2 per pass is not
+    needed here, the 32 MiB queue itself is what a step streams)."""
+    K, D, nf, T = 65536, 128, 4, 0.07
+    F = torch.nn.functional
+    q = F.normalize(torch.randn((B, D), device=dev), dim=1)
+    k = F.normalize(q + 0.5 * torch.randn((B, D), device=dev), dim=1)
+    queues = []
+    for _ in range(3):
+        qu = F.normalize(torch.randn((K, D), device=dev), dim=1)
+        qt = torch.empty_like(qu)
+        ops.round_tf32(qu, qt)
+        queues.append(qt)
+    fwd = [ops.infonce_fwd(q, k, queues[i], nf, T) for i in range(3)]
+    t, tm = timeit([lambda i=i: ops.infonce_fwd(q, k, queues[i], nf, T) for i in range(3)], a.iters)
+    report("infonce_fwd B=%d K=%d D=%d (4 launches)" % (B, K, D), t, tm, 4 * D * (K + 2 * B), flops=2.0 * B * (B + K) * D)
+    t, tm = timeit([lambda i=i: ops.infonce_bwd(q, k, queues[i], nf, T, fwd[i]) for i in range(3)], a.iters)
+    report("infonce_bwd B=%d K=%d D=%d (4 launches)" % (B, K, D), t, tm, 4 * D * (K + 2 * B), flops=4.0 * B * (B + K) * D)
 
 
 def bench_stem(a, dev, B, nbuf):

@@ -194,6 +194,12 @@ def test_infonce_matches_reference_golden(golden, case):
         ref_self = float(g[case + "/nce_loss_self"])
         assert abs(float(losses["nce_loss_self"][1]) - ref_self) / abs(ref_self) < LOSS_TOL
         assert rel(out["vince_loss_self_dists"], g[case + "/self_dists"]) < LOSS_TOL
+    # fused backward: d(nce_loss [+ nce_loss_self])/d(embeddings) vs the reference's autograd result
+    dq = model.embedding_gradients(out)
+    torch.cuda.synchronize()
+    err_dq = rel(dq, g[case + "/dq"])
+    print("%s dq rel-L2 vs reference autograd: %.3e" % (case, err_dq))
+    assert err_dq < 1e-3
     # the lazily materialised similarity matrix equals the reference's
     sims = out["vince_similarities"].materialize()
     assert rel(sims, g[case + "/similarities"]) < 1e-4
@@ -392,6 +398,86 @@ def test_encoder_full_batch_eval_is_batch_separable():
     print("full-batch vs two halves, eval mode: rel-L2 %.2e" % err)
     assert err < 1e-5
     assert rel(full.norm(dim=1), torch.ones(256)) < 1e-6
+
+
+def test_encoder_overlap_is_bitwise_equal_to_serial():
+    """The two-stream schedule (key encoder on the caller's stream, query encoder on a side stream, joined before
+    get_embeddings returns) must not change a single bit, and must only trigger for the batch the fork point saw."""
+    import vince_b200
+    from vince_b200 import vince_model as vm
+    args, model, sd = build_model("ResNet18", 2, 8, 64, 128, seed=3)
+    qm = vince_b200.VinceQueueModel(args, model)
+    qm.to(DEV)
+    qm.train()
+    gen = torch.Generator().manual_seed(11)
+    data = torch.randn((8, 3, 96, 96), generator=gen).to(DEV)
+    queue_data = torch.randn((8, 3, 96, 96), generator=gen).to(DEV)
+    batch = {"data": data, "queue_data": queue_data, "batch_types": ["images"], "batch_sizes": [8]}
+    snap = {k: v.clone() for k, v in model.state_dict().items()}
+    snap_k = {k: v.clone() for k, v in qm.state_dict().items()}
+    results = []
+    for overlap in ("0", "1", "1"):
+        model.load_state_dict(snap)
+        qm.load_state_dict(snap_k)
+        os.environ["VINCE_B200_OVERLAP"] = overlap
+        try:
+            perms = [torch.randperm(8, generator=torch.Generator().manual_seed(5)) for _ in range(2)]
+            with injected_randperm(perms):
+                kb = qm(batch, shuffle=True)[0]
+                qb = model.get_embeddings(batch, shuffle=True)[0]
+            # consumed on the caller's stream with NO device-wide synchronisation in between: the join must be enough
+            out = (qb["embeddings"] + 0).cpu(), (kb["queue_embeddings"] + 0).cpu(), (qb["spatial_features"] + 0).cpu()
+        finally:
+            os.environ.pop("VINCE_B200_OVERLAP", None)
+        results.append(out)
+    for a, b in zip(results[0], results[1]):
+        assert torch.equal(a, b)
+    for a, b in zip(results[0], results[2]):
+        assert torch.equal(a, b)
+    # a fork point recorded for another tensor (or a modified one) must not be used
+    qm(batch, shuffle=False)
+    other = {"data": data.clone(), "batch_types": ["images"], "batch_sizes": [8]}
+    assert vm._take_fork(other["data"]) is None
+    qm(batch, shuffle=False)
+    data.add_(0.0)                      # bumps the version counter
+    assert vm._take_fork(data) is None
+
+
+def test_batch_prefetcher_orders_copies_and_compute():
+    from vince_b200.prefetch import BatchPrefetcher
+    pf = BatchPrefetcher(DEV, depth=2)
+    host = [{"data": torch.full((1 << 20,), float(i)).pin_memory(), "queue_data": torch.full((4,), -float(i)).pin_memory(),
+             "num_frames": 4} for i in range(5)]
+    got = []
+    pf.submit(host[0])
+    for i in range(5):
+        if i + 1 < 5:
+            pf.submit(host[i + 1])
+        b = pf.next()
+        assert b["num_frames"] == 4 and b["queue_data_cpu"] is host[i]["queue_data"]
+        got.append((b["data"].sum() / b["data"].numel(), b["queue_data"].sum()))     # async compute on the batch
+        pf.release(b)
+    with pytest.raises(RuntimeError):
+        pf.next()
+    torch.cuda.synchronize()
+    for i, (m, q) in enumerate(got):
+        assert float(m) == float(i) and float(q) == -4.0 * i
+    assert pf.h2d_bytes == (1 << 20) * 4 + 16
+
+
+def test_fp16_split_saturates_instead_of_overflowing():
+    """Operand planes are fp16 (hi, lo): values beyond +-65504 must saturate, never become inf/NaN."""
+    from vince_b200 import ops
+    x = torch.tensor([0.0, 1.0, -3.14159, 70000.0, -1e9, 6e-8, 1e-3, 65504.0], device=DEV)
+    hi = torch.empty_like(x, dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    ops.split_f16(x, hi, lo)
+    torch.cuda.synchronize()
+    assert torch.isfinite(hi.float()).all() and torch.isfinite(lo.float()).all()
+    back = hi.double() + lo.double()
+    small = x.abs() <= 65504
+    assert ((back[small] - x[small].double()).abs() <= x[small].double().abs() * 2.0 ** -22 + 6e-8).all()
+    assert float(back[3]) == 70000.0 and float(hi[4]) == -65504.0
 
 
 def test_ops_reject_cpu_tensors():

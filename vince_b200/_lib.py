@@ -62,6 +62,8 @@ SIGNATURES = {
     "vince_jigsaw_gather": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "vince_infonce_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "vince_infonce_fwd": (c_int32, [POINTER(InfoNceDesc), c_void_p]),
+    "vince_infonce_bwd_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "vince_infonce_bwd": (c_int32, [POINTER(InfoNceDesc), c_float, c_int32, c_int32, c_void_p, c_void_p]),
     "vince_masked_ce_fwd": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vince_ema_enqueue": (c_int32, [c_void_p, c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int64,

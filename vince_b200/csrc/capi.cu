@@ -146,6 +146,19 @@ int vince_infonce_fwd(const vince_infonce_desc* d, void* stream) {
   return infonce_fwd_launch(n, S(stream));
 }
 
+size_t vince_infonce_bwd_workspace_bytes(int32_t B, int32_t D) { return infonce_bwd_workspace_bytes(B, D); }
+
+int vince_infonce_bwd(const vince_infonce_desc* d, float grad_dist, int32_t symmetric, int32_t accumulate, float* dq,
+                      void* stream) {
+  VB_REQUIRE(d != nullptr, "vince_infonce_bwd: null descriptor");
+  InfoNceDesc n;
+  memset(&n, 0, sizeof(n));
+  n.q = d->q, n.keys = d->keys, n.queue_tf32 = d->queue_tf32;
+  n.B = d->B, n.Bk = d->Bk, n.K = d->K, n.D = d->D, n.num_frames = d->num_frames, n.temperature = d->temperature;
+  n.pos_sim = d->pos_sim, n.row_lse = d->row_lse, n.workspace = d->workspace;
+  return infonce_bwd_launch(n, grad_dist, symmetric, accumulate, dq, S(stream));
+}
+
 int vince_masked_ce_fwd(const float* sims, const uint8_t* mask, int32_t rows, int32_t cols, int32_t n_pos,
                         float temperature, float* dists, float* weights, float* pos_sim, float* neg_max, float* row_lse,
                         float* scalars, int32_t* error_flag, void* stream) {

@@ -118,6 +118,11 @@ struct InfoNceDesc {
 size_t infonce_workspace_bytes(int B, int D);
 int infonce_fwd_launch(const InfoNceDesc& d, cudaStream_t stream);
 int round_tf32_launch(const float* x, float* out, int64_t n, cudaStream_t stream);
+// backward w.r.t. q (infonce_bwd.cu): d.pos_sim / d.row_lse are the forward's outputs (inputs here); symmetric = the
+// self-batch loss where the columns are the queries themselves; accumulate adds to dq instead of overwriting it
+size_t infonce_bwd_workspace_bytes(int B, int D);
+int infonce_bwd_launch(const InfoNceDesc& d, float grad_dist, int symmetric, int accumulate, float* dq,
+                       cudaStream_t stream);
 // explicit-matrix masked cross entropy (loss_util.similarity_cross_entropy's literal signature); error_flag is set
 // to 1 when some row does not have exactly nP positives
 int masked_ce_launch(const float* sims, const uint8_t* mask, int R, int C, int nP, float temperature, float* dists,

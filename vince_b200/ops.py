@@ -292,6 +292,35 @@ def infonce_fwd(q, keys, queue_tf32, num_frames, temperature, workspace=None):
     return out
 
 
+def infonce_bwd(q, keys, queue_tf32, num_frames, temperature, fwd, grad_dist=1.0, symmetric=False, dq=None,
+                accumulate=False):
+    """d(grad_dist * dist)/dq for the fused InfoNCE loss (what autograd produces through vince_model.py:213-233 +
+    loss_util.py:7-62); `fwd` is the dict returned by infonce_fwd for the same operands.  symmetric=True is the
+    self-batch loss (keys is q itself, no queue) whose columns carry gradient too.  Returns dq [B, D]."""
+    B, D = q.shape
+    K = 0 if queue_tf32 is None else queue_tf32.shape[0]
+    dev = q.device
+    if dq is None:
+        if accumulate:
+            raise ValueError("infonce_bwd: accumulate needs an existing dq")
+        dq = torch.empty((B, D), device=dev, dtype=torch.float32)
+    workspace = torch.empty((int(_lib.lib().vince_infonce_bwd_workspace_bytes(B, D)),), device=dev, dtype=torch.uint8)
+    d = _lib.InfoNceDesc()
+    d.q = _val(q, torch.float32, "q")
+    d.keys = _val(keys, torch.float32, "keys")
+    d.queue_tf32 = _val(queue_tf32, torch.float32, "queue_tf32") if K > 0 else None
+    d.B, d.Bk, d.K, d.D, d.num_frames = B, keys.shape[0], K, D, num_frames
+    d.temperature = float(temperature)
+    d.pos_sim = _val(fwd["pos_sim"], torch.float32, "pos_sim")
+    d.row_lse = _val(fwd["row_lse"], torch.float32, "row_lse")
+    d.workspace = _val(workspace, torch.uint8, "workspace")
+    _lib.check(_lib.lib().vince_infonce_bwd(ctypes.byref(d), float(grad_dist), 1 if symmetric else 0,
+                                            1 if accumulate else 0, _ptr(dq, torch.float32, "dq"), _stream()),
+               "vince_infonce_bwd")
+    dq._workspace = workspace        # keep alive until the stream has consumed it
+    return dq
+
+
 def ema_enqueue(table_dev, n_chunks, momentum, queue=None, queue_tf32=None, keys=None, tail=0):
     """theta_k <- m theta_k + (1-m) theta_q over the chunk table and, if keys is given, ring-buffer enqueue at
     `tail` following storage_queue.py:31-49.  Returns (new_tail, wrapped)."""

@@ -32,6 +32,65 @@ def _device_of(t):
     return t if isinstance(t, torch.device) else torch.device(t)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Encoder overlap.  The key-encoder forward (VinceQueueModel.__call__, vince_solver.py:405) and the query-encoder
+# forward (VinceModel.get_embeddings, :406) are independent; each alternates tensor-core-bound convolutions with
+# HBM-bound BatchNorm/ReLU passes, so running them on two CUDA streams lets one encoder's streaming kernels fill the
+# memory pipe while the other's convolutions own the tensor cores.
+#
+# Safe by construction - nothing asynchronous ever leaks out of an API call: VinceQueueModel.forward only RECORDS a
+# fork event on the caller's stream before launching the key encoder there (as always); the next
+# VinceModel.get_embeddings on the same device, if it is handed the very batch tensor the fork saw (same storage,
+# same version counter), runs the query encoder on a private side stream that waits for the fork event only, and the
+# caller's stream waits for the side stream before get_embeddings returns.  Everything the caller launches afterwards
+# is therefore ordered after BOTH encoders.  Any other call order simply runs on the caller's stream.
+# Disable with args.vince_b200_overlap_encoders = False or VINCE_B200_OVERLAP=0.
+# ---------------------------------------------------------------------------------------------------------------
+_FORK = {}            # device index -> (event, data_ptr, version) recorded by the last VinceQueueModel.forward
+_SIDE_STREAMS = {}    # device index -> torch.cuda.Stream
+
+
+def _overlap_enabled(args):
+    if os.environ.get("VINCE_B200_OVERLAP", "1") == "0":
+        return False
+    return bool(getattr(args, "vince_b200_overlap_encoders", True))
+
+
+def _record_fork(inputs):
+    data = inputs.get("data") if isinstance(inputs, dict) else None
+    if not isinstance(data, torch.Tensor) or not data.is_cuda:
+        return
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(data.device))
+    _FORK[data.device.index] = (ev, data.data_ptr(), data._version)
+
+
+def _take_fork(data):
+    fork = _FORK.pop(data.device.index, None)
+    if fork is None or fork[1] != data.data_ptr() or fork[2] != data._version:
+        return None
+    return fork[0]
+
+
+def _side_stream(device):
+    st = _SIDE_STREAMS.get(device.index)
+    if st is None:
+        st = _SIDE_STREAMS[device.index] = torch.cuda.Stream(device=device)
+    return st
+
+
+def _record_stream_all(obj, stream):
+    if isinstance(obj, torch.Tensor):
+        if obj.is_cuda:
+            obj.record_stream(stream)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _record_stream_all(v, stream)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            _record_stream_all(v, stream)
+
+
 class BaseModel(nn.Module):
     """Stand-in for dg_util's pt_util.BaseModel + models/base_model.py:8-26 (device bookkeeping, save/restore)."""
 
@@ -219,14 +278,30 @@ class VinceModel(BaseModel):
             return_val["extracted_features"] = pooled
         return return_val
 
-    def get_embeddings(self, inputs, jigsaw=False, shuffle=False, jigsaw_orders=None):
-        """vince_model.py:135-196.  `jigsaw_orders` ([N,9] int64, optional) replaces the per-row randperm(9) draw."""
+    def get_embeddings(self, inputs, jigsaw=False, shuffle=False, jigsaw_orders=None, _may_overlap=True):
+        """vince_model.py:135-196.  `jigsaw_orders` ([N,9] int64, optional) replaces the per-row randperm(9) draw.
+        Runs on a side stream, concurrently with a key-encoder forward launched just before on the caller's stream,
+        when that is provably safe (see "Encoder overlap" at the top of this file)."""
+        data = inputs["data"]
+        if not data.is_cuda:
+            raise RuntimeError("vince_b200.VinceModel: input batch must already be on the GPU (the solver's "
+                               "prefetch thread does the H2D copy, vince_solver.py:352-355); no CPU fallback")
+        fork = _take_fork(data) if (_may_overlap and _overlap_enabled(self.args)) else None
+        if fork is None:
+            return self._get_embeddings(inputs, jigsaw, shuffle, jigsaw_orders)
+        main = torch.cuda.current_stream(data.device)
+        side = _side_stream(data.device)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            return_val = self._get_embeddings(inputs, jigsaw, shuffle, jigsaw_orders)
+        _record_stream_all(return_val, main)      # allocated on the side stream, consumed (and freed) on the caller's
+        main.wait_stream(side)
+        return return_val
+
+    def _get_embeddings(self, inputs, jigsaw, shuffle, jigsaw_orders):
         self.launches = 0
         with torch.no_grad():
             data = inputs["data"]
-            if not data.is_cuda:
-                raise RuntimeError("vince_b200.VinceModel: input batch must already be on the GPU (the solver's "
-                                   "prefetch thread does the H2D copy, vince_solver.py:352-355); no CPU fallback")
             n = data.shape[0]
             shuffle_order = None
             if shuffle:
@@ -324,9 +399,11 @@ class VinceModel(BaseModel):
                     self.launches += 1
                 fused = {"main": ops.infonce_fwd(output_k, queue_embeddings_k, queue_tf32, nf,
                                                 self.args.vince_temperature)}
+                fused["main"]["_operands"] = (output_k, queue_embeddings_k, queue_tf32, nf, self.args.vince_temperature)
                 self.launches += 4 if ibc else 3
                 if ibc and self.args.self_batch_comparison:
                     fused["self"] = ops.infonce_fwd(output_k, output_k, None, nf, self.args.vince_self_temperature)
+                    fused["self"]["_operands"] = (output_k, output_k, None, nf, self.args.vince_self_temperature)
                     self.launches += 4
                     return_val["vince_self_similarities"] = LazySimilarity(output, [output])
                     return_val["vince_self_similarities_mask"] = None
@@ -378,6 +455,24 @@ class VinceModel(BaseModel):
                 network_outputs.update({"vince_loss_self_" + key: val for key, val in sl.items()})
                 losses["nce_loss_self"] = (1.0, sl["dist"])
         return losses
+
+    def embedding_gradients(self, network_outputs: Dict, loss_weights: Optional[Dict[str, float]] = None):
+        """d(sum of weighted losses)/d(embeddings) [B, D] with the fused backward kernel: the tensor autograd hands to
+        the projection head when vince_solver.py:465 calls loss.backward() (keys / queue are detached,
+        vince_model.py:598,610).  `loss_weights` maps "nce_loss" / "nce_loss_self" to their weights (default 1.0, as
+        VinceModel.loss returns).  Autograd itself does not flow through the CUDA path (module docstring)."""
+        fused = network_outputs["_vince_fused"]
+        loss_weights = loss_weights or {}
+        dq = None
+        with torch.no_grad(), torch.cuda.device(network_outputs["embeddings"].device):
+            for key, lname in (("main", "nce_loss"), ("self", "nce_loss_self")):
+                if key not in fused:
+                    continue
+                q, keys, queue_tf32, nf, T = fused[key]["_operands"]
+                dq = ops.infonce_bwd(q, keys, queue_tf32, nf, T, fused[key], grad_dist=loss_weights.get(lname, 1.0),
+                                     symmetric=(key == "self"), dq=dq, accumulate=dq is not None)
+        D = network_outputs["embeddings"].shape[1]
+        return dq[:, :D] if dq.shape[1] != D else dq
 
     def get_metrics(self, network_outputs: Optional[Dict]) -> Dict[str, Optional[float]]:
         with torch.no_grad():
@@ -479,11 +574,13 @@ class VinceQueueModel(BaseModel):
     def forward(self, inputs, jigsaw=False, shuffle=True, jigsaw_orders=None):
         with torch.no_grad():
             queue_data = inputs["queue_data"]
+            if _overlap_enabled(self.args):
+                _record_fork(inputs)          # lets the query encoder that follows run beside this one
             sub = {"data": queue_data}
             if "batch_types" in inputs:
                 sub.update({"batch_types": inputs["batch_types"], "batch_sizes": inputs["batch_sizes"]})
             output_mini_batches = self.queue_network.get_embeddings(sub, jigsaw=jigsaw, shuffle=shuffle,
-                                                                    jigsaw_orders=jigsaw_orders)
+                                                                    jigsaw_orders=jigsaw_orders, _may_overlap=False)
             self.launches = self.queue_network.launches
             single = isinstance(output_mini_batches, dict)
             if single:
