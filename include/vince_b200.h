@@ -106,7 +106,7 @@ typedef struct {
   int32_t scale_log2;     /* weights are multiplied by 2^scale_log2 before the split, so that the lo plane of O(1e-2)
                            * weights stays a normal fp16 number; pass alpha = 2^-scale_log2 to vince_conv_fwd */
 } vince_weight_entry;
-int vince_weight_prep(const vince_weight_entry* table_dev, int32_t n_entries, int64_t max_elems, void* w_hi, void* w_lo,
+int vince_weight_prep(const vince_weight_entry* table_dev, int32_t n_entries, int64_t max_cout, void* w_hi, void* w_lo,
                       void* stream);
 
 /* ---- BatchNorm apply (+residual, +ReLU) and pooling ----------------------------------------------------------

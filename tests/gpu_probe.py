@@ -53,7 +53,7 @@ def prep_weight(w, kind=0):
     hi = torch.empty((Cout, K), device=DEV, dtype=torch.float16)
     lo = torch.empty_like(hi)
     tab = weight_table([(w, 0, Cout, Cin, R, S, kind)])
-    ops.weight_prep(tab, 1, Cout * K, hi, lo)
+    ops.weight_prep(tab, 1, Cout, hi, lo)
     torch.cuda.synchronize()
     return hi, lo
 

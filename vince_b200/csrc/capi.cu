@@ -65,11 +65,12 @@ int vince_stem_pack(const float* x, const int64_t* gather_idx, void* x_hi, void*
   return stem_pack_launch(x, gather_idx, HF(x_hi), HF(x_lo), N, H, W, (H - 1) / 2 + 4, (W - 1) / 2 + 4, S(stream));
 }
 
-int vince_weight_prep(const vince_weight_entry* table_dev, int32_t n_entries, int64_t max_elems, void* w_hi, void* w_lo,
+int vince_weight_prep(const vince_weight_entry* table_dev, int32_t n_entries, int64_t max_cout, void* w_hi, void* w_lo,
                       void* stream) {
   static_assert(sizeof(vince_weight_entry) == sizeof(WeightPrepEntry), "ABI struct mismatch");
   VB_REQUIRE(n_entries == 0 || (table_dev && w_hi), "vince_weight_prep: null pointer");
-  return weight_prep_launch(reinterpret_cast<const WeightPrepEntry*>(table_dev), n_entries, max_elems, HF(w_hi),
+  VB_REQUIRE(max_cout >= 0 && max_cout <= 0x7fffffff, "vince_weight_prep: bad max_cout");
+  return weight_prep_launch(reinterpret_cast<const WeightPrepEntry*>(table_dev), n_entries, (int)max_cout, HF(w_hi),
                             HF(w_lo), S(stream));
 }
 

@@ -36,7 +36,7 @@ constexpr int EPI_WARP0 = 5;            // first epilogue warp
 constexpr int EPI_TID0 = EPI_WARP0 * 32;
 constexpr int MAX_RING = 8;
 constexpr int STAGING_BYTES = BM * 128;   // 128 rows x 32 fp32
-constexpr size_t SMEM_BUDGET = 224 * 1024;    // leaves room on the SM for co-resident streaming kernels of the other encoder
+constexpr size_t SMEM_BUDGET = 226 * 1024;    // of 227 KB: leaves the 1 KB system reservation of one co-resident block
 
 struct GemmKernelParams {
   CUtensorMap a_hi, a_lo, b_hi, b_lo, out;
@@ -109,7 +109,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 // fits in shared memory next to the activation ring, so it is loaded ONCE per CTA; afterwards only activations
 // stream and the issuing thread waits on / commits to one barrier per activation stage instead of one per k-block.
 template <int BN, int CG, bool HALO, bool RES>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
+__global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -694,6 +694,12 @@ static int auto_block_n(const ConvGemmDesc& d, int cg) {
   int best = 64;
   for (int bn : cands) {
     if (bn > 64 && d.N % bn != 0) continue;
+    {
+      // a 2-stage ring of (A tile + this CTA's weight share) must fit next to the fixed buffers
+      const size_t planes = d.passes == 3 ? 2 : 1;
+      const size_t stage = ((size_t)BM * 128 + (size_t)(bn / cg) * 128) * planes;
+      if (bn > 64 && fixed_smem(bn) + 2 * stage > SMEM_BUDGET) continue;
+    }
     const long tiles = m_blocks * ((d.N + bn - 1) / bn);
     const long waves = (tiles + units - 1) / units;
     const long passes = d.passes == 3 ? 3 : 1;

@@ -218,6 +218,18 @@ __global__ void __launch_bounds__(NCE_THREADS, 1) infonce_main_kernel(const __gr
   }
 }
 
+// round-to-nearest fp32 -> tf32 of two arrays in one launch (queries and keys of the fused loss)
+__global__ void round_tf32_pair_kernel(const float* __restrict__ x0, float* __restrict__ o0, int64_t n0,
+                                       const float* __restrict__ x1, float* __restrict__ o1, int64_t n1) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = i < n0 ? x0[i] : x1[i - n0];
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    if (i < n0) o0[i] = __uint_as_float(u);
+    else o1[i - n0] = __uint_as_float(u);
+  }
+}
+
 // round-to-nearest fp32 -> tf32 (kept in an fp32 container)
 __global__ void round_tf32_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -334,11 +346,13 @@ int infonce_fwd_launch(const InfoNceDesc& d, cudaStream_t stream) {
   float* k_r = q_r + (size_t)nmb * NCE_BM * d.D;
   float2* partials = reinterpret_cast<float2*>(k_r + (size_t)nmb * NCE_BM * d.D);
 
-  int rc = round_tf32_launch(d.q, q_r, (int64_t)d.B * d.D, stream);
-  if (rc) return rc;
-  if (ibc) {
-    rc = round_tf32_launch(d.keys, k_r, (int64_t)d.Bk * d.D, stream);
-    if (rc) return rc;
+  int rc = VB_OK;
+  {
+    const int64_t n0 = (int64_t)d.B * d.D, n1 = ibc ? (int64_t)d.Bk * d.D : 0;
+    int64_t blocks = (n0 + n1 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    round_tf32_pair_kernel<<<(int)blocks, 256, 0, stream>>>(d.q, q_r, n0, d.keys, k_r, n1);
+    VB_CHECK_CUDA(cudaGetLastError());
   }
 
   NceParams kp;

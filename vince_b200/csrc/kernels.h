@@ -58,7 +58,7 @@ struct WeightPrepEntry {   // one per weight tensor; lives in device memory
   int32_t kind;            // 0: [Cout][R][S][Cin]; 1: stem packing [64][4][4][16]
   int32_t scale_log2;      // weights are multiplied by 2^scale_log2 before the fp16 split (keeps lo planes normal)
 };
-int weight_prep_launch(const WeightPrepEntry* table_dev, int n_entries, int64_t max_elems, __half* hi,
+int weight_prep_launch(const WeightPrepEntry* table_dev, int n_entries, int max_cout, __half* hi,
                        __half* lo, cudaStream_t stream);
 
 struct BnSide {

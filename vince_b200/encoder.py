@@ -56,7 +56,7 @@ class WeightBank:
             s.w_off = off
             off = _align(off + s.Cout * s.K, 64)
         self.total = off
-        self.max_elems = max((s.Cout * s.K for s in specs), default=0)
+        self.max_cout = max((s.Cout for s in specs), default=0)
         self.device = None
         self._ptrs = None
         self.w_hi = self.w_lo = self.table = self._run = None
@@ -83,7 +83,7 @@ class WeightBank:
         self.table = torch.from_numpy(arr.view(np.uint8).copy()).to(dev)
         self.w_hi = torch.empty((self.total,), device=dev, dtype=torch.float16)
         self.w_lo = torch.empty((self.total,), device=dev, dtype=torch.float16) if self.passes == 3 else None
-        self._run = ops.build_weight_prep(self.table, len(self.specs), self.max_elems, self.w_hi, self.w_lo)
+        self._run = ops.build_weight_prep(self.table, len(self.specs), self.max_cout, self.w_hi, self.w_lo)
         self._ptrs, self.device = ptrs, dev
         self.generation += 1
 

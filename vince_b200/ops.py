@@ -156,9 +156,10 @@ def stem_pack(*a):
     build_stem_pack(*a)()
 
 
-def build_weight_prep(table_dev, n_entries, max_elems, w_hi, w_lo):
+def build_weight_prep(table_dev, n_entries, max_cout, w_hi, w_lo):
+    """max_cout: largest Cout over the table (one block per output channel and tensor)"""
     run = _bind(_lib.lib().vince_weight_prep, "vince_weight_prep", _ptr(table_dev, torch.uint8, "table"), n_entries,
-                max_elems, _ptr(w_hi, torch.float16, "w_hi"), _ptr(w_lo, torch.float16, "w_lo"))
+                max_cout, _ptr(w_hi, torch.float16, "w_hi"), _ptr(w_lo, torch.float16, "w_lo"))
     run._keep = (table_dev, w_hi, w_lo)
     return run
 

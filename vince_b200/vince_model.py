@@ -521,6 +521,7 @@ class VinceQueueModel(BaseModel):
             param.requires_grad = False
         self._ema_table = None
         self._ema_key = None
+        self._ema_probe = None
         self.launches = 0
 
     def to(self, device):
@@ -530,9 +531,15 @@ class VinceQueueModel(BaseModel):
 
     def _table(self, encoder_model):
         import numpy as np
+        # fast path (every training step): same encoder object and its / our first and last parameters still live
+        # where the cached table says (a device move or re-allocation changes all of them)
+        probe = self._ema_probe
+        if probe is not None and probe[0] is encoder_model and all(p.data_ptr() == ptr for p, ptr in probe[1]):
+            return self._ema_table
         dst = self.queue_network.vince_parameters()
         src = encoder_model.vince_parameters()
         key = tuple(p.data_ptr() for p in dst) + tuple(p.data_ptr() for p in src)
+        self._ema_probe = (encoder_model, [(p, p.data_ptr()) for p in (dst[0], dst[-1], src[0], src[-1])])
         if self._ema_key != key:
             chunks = []
             for d, s in zip(dst, src):
@@ -554,7 +561,7 @@ class VinceQueueModel(BaseModel):
         """vince_model.py:587-592 as ONE launch.  `enqueue=(storage_queue, keys, images, data_source)` additionally
         performs StorageQueue.enqueue in the same launch (the reference does it just before, vince_solver.py:497)."""
         table, n = self._table(encoder_model)
-        dev = self.queue_network.vince_parameters()[0].device
+        dev = table.device
         with torch.no_grad(), torch.cuda.device(dev):
             if enqueue is None:
                 ops.ema_enqueue(table, n, momentum)
