@@ -315,7 +315,10 @@ def run_ours(a):
         "note": "algorithmic FLOPs = 2*M*N*K of the fp32 conv; the kernel issues 3 fp16 MMAs per k-step to reach "
                 "fp32-grade accuracy, so frac <= 1/3 by construction",
     }
-    cpu = cpu_baseline(wl, seconds=15.0)
+    # the CPU leg is a property of the box, not of N: measured on rank 0 of the N=1 run only
+    cpu = cpu_baseline(wl, seconds=15.0) if world == 1 else {
+        "value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+        "sample": "not measured at N>1 (see the N=1 line of the same run, or --impl reference)"}
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": round(ms / a.steps, 4), "higher_is_better": True, "scaling": "weak",

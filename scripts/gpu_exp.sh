@@ -1,13 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-{
-echo "== probes"; timeout 600 python tests/gpu_probe.py 2>&1 | grep -v PASS | tail -12
-echo "== stem"; timeout 120 python tests/elem_bench.py --only stem
-echo "== nce"; timeout 120 python tests/elem_bench.py --only nce
-echo "== pytest"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-echo "== bench"; timeout 600 python bench.py --steps 50 --warmup 5 2> gpurun_out/bench.err | tee gpurun_out/bench.json | python -c "
-import json,sys
-d=json.loads(sys.stdin.read())
-print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],'nce ms',d['infonce_step_ms'],'iso ms',d['roofline']['isolated']['ms_per_step'],'iso frac',d['roofline']['isolated']['frac'],'clk',d['clocks'])"
-tail -3 gpurun_out/bench.err
-} 2>&1 | tee gpurun_out/exp.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 3 -c 1 -o gpurun_out/l1_default -f python tests/conv_bench.py --filter r18.layer1 --iters 2 > gpurun_out/ncu_l1.log 2>&1
+VINCE_B200_DEBUG_SKIP_MMA=7 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 3 -c 1 -o gpurun_out/l1_skel -f python tests/conv_bench.py --filter r18.layer1 --iters 2 >> gpurun_out/ncu_l1.log 2>&1
+tail -3 gpurun_out/ncu_l1.log; ls -la gpurun_out/*.ncu-rep
