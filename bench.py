@@ -210,6 +210,8 @@ def run_ours(a):
         gather = KeyGather(dev)
     from vince_b200 import ops
     wl = dict(WORKLOAD)
+    if a.backbone == "ResNet50":
+        wl.update(backbone="ResNet50", T=0.2)
     hp = HotPath(dev, wl, rank, world, gather)
 
     def barrier():
@@ -324,8 +326,8 @@ def run_ours(a):
         "warmup": max(a.warmup, 3), "ms_per_step": round(ms / a.steps, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (fp16x3 split MMA, fp32 accumulate; TF32 for InfoNCE negatives)",
         "data": "synthetic",
-        "config": {"workload": "BASELINE.json configs[1]: ResNet18, 4 views/clip, batch=256 frames/GPU, queue K=65536, "
-                               "dim=128, 224x224", "per_gpu_batch": wl["B"], "frames_per_step": frames_per_step,
+        "config": {"workload": "BASELINE.json configs[%d]: %s, 4 views/clip, batch=256 frames/GPU, queue K=65536, "
+                               "dim=128, 224x224" % (1 if wl["backbone"] == "ResNet18" else 2, wl["backbone"]), "per_gpu_batch": wl["B"], "frames_per_step": frames_per_step,
                    "parallelism": "dp%d (replicated weights+queue, NCCL all-gather of keys)" % world if world > 1 else "single GPU",
                    "streams": "key encoder on the caller's stream, query encoder on a side stream (joined before "
                               "get_embeddings returns); VINCE_B200_OVERLAP=0 serialises them",
@@ -394,6 +396,8 @@ def run_reference(a):
     if rank != 0:
         return
     wl = dict(WORKLOAD)
+    if a.backbone == "ResNet50":
+        wl.update(backbone="ResNet50", T=0.2)
     B = 32
     step = cpu_step_runner(wl, B)
     for _ in range(max(1, min(a.warmup, 2))):
@@ -409,8 +413,8 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
             "steps": steps, "warmup": max(1, min(a.warmup, 2)), "ms_per_step": round(dt / steps * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE.json configs[1]: ResNet18, 4 views/clip, queue K=65536, dim=128, 224x224; "
-                                   "CPU sample batch=32 frames"},
+            "config": {"workload": "BASELINE.json configs[%d]: %s, 4 views/clip, queue K=65536, dim=128, 224x224; "
+                                   "CPU sample batch=32 frames" % (1 if wl["backbone"] == "ResNet18" else 2, wl["backbone"])},
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -422,6 +426,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--backbone", default="ResNet18", choices=["ResNet18", "ResNet50"],
+                    help="ResNet18 = BASELINE.json configs[1] (the bench contract's workload, default); ResNet50 = configs[2] "
+                         "(MoCoV2 config, T=0.2), an extra line for the record")
     ap.add_argument("--profile-only", action="store_true",
                     help="stop after the device-resident timed steps (for runs under ncu; prints no bench value)")
     a = ap.parse_args()

@@ -27,6 +27,8 @@ SHAPES = [
     ("r18.layer4.ds 1x1/2", 14, 14, 256, 512, 1, 2, 0),
     ("r50.layer1 1x1 64->256", 56, 56, 64, 256, 1, 1, 0),
     ("r50.layer1 1x1 256->64", 56, 56, 256, 64, 1, 1, 0),
+    ("r50.layer2 1x1 128->512", 28, 28, 128, 512, 1, 1, 0),
+    ("r50.layer2 1x1 512->128", 28, 28, 512, 128, 1, 1, 0),
     ("r50.layer3 1x1 1024->256", 14, 14, 1024, 256, 1, 1, 0),
     ("r50.layer4 1x1 512->2048", 7, 7, 512, 2048, 1, 1, 0),
 ]
