@@ -123,9 +123,14 @@ class HotPath:
         self.qm.train()
         self.queue = vince_b200.StorageQueue(wl["K"], wl["D"], device=dev)
         g = torch.Generator().manual_seed(1234 + rank)
-        shape = (wl["B"], 3, wl["H"], wl["H"])
-        self.host_data = torch.randn(shape, generator=g).pin_memory()
-        self.host_queue_data = torch.randn(shape, generator=g).pin_memory()
+        if wl.get("input", "fp32") == "uint8":
+            shape = (wl["B"], wl["H"], wl["H"], 3)
+            self.host_data = torch.randint(0, 256, shape, generator=g, dtype=torch.uint8).pin_memory()
+            self.host_queue_data = torch.randint(0, 256, shape, generator=g, dtype=torch.uint8).pin_memory()
+        else:
+            shape = (wl["B"], 3, wl["H"], wl["H"])
+            self.host_data = torch.randn(shape, generator=g).pin_memory()
+            self.host_queue_data = torch.randn(shape, generator=g).pin_memory()
         self.dev_data = self.host_data.to(dev)
         self.dev_queue_data = self.host_queue_data.to(dev)
         self.launches = 0
@@ -212,6 +217,7 @@ def run_ours(a):
     wl = dict(WORKLOAD)
     if a.backbone == "ResNet50":
         wl.update(backbone="ResNet50", T=0.2)
+    wl["input"] = a.input
     hp = HotPath(dev, wl, rank, world, gather)
 
     def barrier():
@@ -329,6 +335,8 @@ def run_ours(a):
         "config": {"workload": "BASELINE.json configs[%d]: %s, 4 views/clip, batch=256 frames/GPU, queue K=65536, "
                                "dim=128, 224x224" % (1 if wl["backbone"] == "ResNet18" else 2, wl["backbone"]), "per_gpu_batch": wl["B"], "frames_per_step": frames_per_step,
                    "parallelism": "dp%d (replicated weights+queue, NCCL all-gather of keys)" % world if world > 1 else "single GPU",
+                   "input": "fp32 NCHW normalised frames (the reference's wire format)" if a.input == "fp32" else
+                            "uint8 HWC raw frames, ToTensor+Normalize fused into the stem packing",
                    "streams": "key encoder on the caller's stream, query encoder on a side stream (joined before "
                               "get_embeddings returns); VINCE_B200_OVERLAP=0 serialises them",
                    "l2_policy": "inputs larger than L2: 2 x 154 MB of fp32 frames + >1 GB of activations per step"},
@@ -429,6 +437,9 @@ def main():
     ap.add_argument("--backbone", default="ResNet18", choices=["ResNet18", "ResNet50"],
                     help="ResNet18 = BASELINE.json configs[1] (the bench contract's workload, default); ResNet50 = configs[2] "
                          "(MoCoV2 config, T=0.2), an extra line for the record")
+    ap.add_argument("--input", default="fp32", choices=["fp32", "uint8"],
+                    help="fp32 = the reference's wire format (normalised NCHW frames, default); uint8 = raw HWC frames with "
+                         "the normalisation fused into the stem packing (SURVEY.md 8f rank 3), an extra line for the record")
     ap.add_argument("--profile-only", action="store_true",
                     help="stop after the device-resident timed steps (for runs under ncu; prints no bench value)")
     a = ap.parse_args()

@@ -96,6 +96,13 @@ int vince_bn_eval_coef(const float* gamma, const float* beta, const float* runni
 int vince_stem_pack(const float* x, const int64_t* gather_idx, void* x_hi, void* x_lo, int32_t N, int32_t H, int32_t W,
                     void* stream);
 
+/* Same packing straight from uint8 HWC frames [N,H,W,3] (what the dataset workers hold before
+ * utils/transforms.py:89-101 applies ToTensor(scale=255) + Normalize): ((x / 255) - mean3[c]) / std3[c] in fp32, same
+ * operation order, fused into the packing (1 byte per element over PCIe / HBM instead of 4).
+ * mean3 / std3 are HOST arrays of 3 floats (constants.py:28-29 divided by 255 for the reference's pipelines). */
+int vince_stem_pack_u8(const uint8_t* x_nhwc, const int64_t* gather_idx, const float* mean3, const float* std3,
+                       void* x_hi, void* x_lo, int32_t N, int32_t H, int32_t W, void* stream);
+
 /* ---- weight preparation (multi-tensor): OIHW fp32 -> K-major fp16 (hi, lo) ----------------------------------
  * replaces: nothing in the reference (cuDNN consumes OIHW directly); run after every weight update. */
 typedef struct {

@@ -443,6 +443,29 @@ def test_encoder_overlap_is_bitwise_equal_to_serial():
     assert vm._take_fork(data) is None
 
 
+def test_uint8_hwc_input_equals_normalised_fp32_input():
+    """raw uint8 HWC frames with ToTensor(scale=255) + Normalize (utils/transforms.py:89-101) fused
+    into the stem packing must give bit-identical results to feeding the frames normalised on the host."""
+    from vince_b200 import ops
+    args, model, sd = build_model("ResNet18", 2, 6, 64, 128, seed=4)
+    gen = torch.Generator().manual_seed(21)
+    for (H, W) in ((96, 96), (75, 51)):
+        x8 = torch.randint(0, 256, (6, H, W, 3), generator=gen, dtype=torch.uint8)
+        mean = torch.tensor(ops.IMAGENET_MEAN).view(1, 3, 1, 1)
+        std = torch.tensor(ops.IMAGENET_STD).view(1, 3, 1, 1)
+        xf = ((x8.permute(0, 3, 1, 2).float() / 255.0) - mean) / std          # ToTensor(scale=255) + Normalize
+        perm = torch.randperm(6, generator=gen)
+        snap = {k: v.clone() for k, v in model.state_dict().items()}
+        outs = []
+        for x in (xf.contiguous(), x8):
+            model.load_state_dict(snap)
+            with injected_randperm([perm]):
+                outs.append(model.get_embeddings({"data": x.to(DEV)}, shuffle=True))
+        torch.cuda.synchronize()
+        for key in ("embeddings", "extracted_features", "spatial_features"):
+            assert torch.equal(outs[0][key], outs[1][key]), key
+
+
 def test_batch_prefetcher_orders_copies_and_compute():
     from vince_b200.prefetch import BatchPrefetcher
     pf = BatchPrefetcher(DEV, depth=2)

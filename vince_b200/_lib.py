@@ -47,6 +47,8 @@ SIGNATURES = {
     "vince_abi_version": (c_int32, []),
     "vince_conv_fwd": (c_int32, [POINTER(ConvDesc), c_void_p]),
     "vince_stem_pack": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "vince_stem_pack_u8": (c_int32, [c_void_p, c_void_p, POINTER(c_float), POINTER(c_float), c_void_p, c_void_p, c_int32,
+                                     c_int32, c_int32, c_void_p]),
     "vince_weight_prep": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
     "vince_bn_eval_coef": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int32, c_void_p]),
     "vince_bn_apply": (c_int32, [POINTER(BnSide), c_int32, c_void_p, c_void_p, POINTER(BnSide), c_int32, c_void_p,

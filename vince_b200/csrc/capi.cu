@@ -65,6 +65,14 @@ int vince_stem_pack(const float* x, const int64_t* gather_idx, void* x_hi, void*
   return stem_pack_launch(x, gather_idx, HF(x_hi), HF(x_lo), N, H, W, (H - 1) / 2 + 4, (W - 1) / 2 + 4, S(stream));
 }
 
+int vince_stem_pack_u8(const uint8_t* x_nhwc, const int64_t* gather_idx, const float* mean3, const float* std3,
+                       void* x_hi, void* x_lo, int32_t N, int32_t H, int32_t W, void* stream) {
+  VB_REQUIRE(x_nhwc && x_hi && mean3 && std3, "vince_stem_pack_u8: null pointer");
+  VB_REQUIRE(N >= 0 && H > 0 && W > 0, "vince_stem_pack_u8: bad shape N=%d H=%d W=%d", N, H, W);
+  return stem_pack_u8_launch(x_nhwc, gather_idx, mean3, std3, HF(x_hi), HF(x_lo), N, H, W, (H - 1) / 2 + 4,
+                             (W - 1) / 2 + 4, S(stream));
+}
+
 int vince_weight_prep(const vince_weight_entry* table_dev, int32_t n_entries, int64_t max_cout, void* w_hi, void* w_lo,
                       void* stream) {
   static_assert(sizeof(vince_weight_entry) == sizeof(WeightPrepEntry), "ABI struct mismatch");

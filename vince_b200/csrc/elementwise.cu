@@ -88,6 +88,69 @@ __global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict_
   }
 }
 
+// uint8 HWC frames (what the dataset workers hold before ToTensor + Normalize, utils/transforms.py:89-101): the
+// normalisation ((x / 255) - mean[c]) / std[c] - the same fp32 operations in the same order - is fused into the
+// packing, so a step moves 1 byte per input element over PCIe and HBM instead of 4.
+struct StemNorm {
+  float mean[3], std[3];
+};
+__global__ void __launch_bounds__(256) stem_pack_u8_kernel(const uint8_t* __restrict__ x,
+                                                           const int64_t* __restrict__ gather_idx, StemNorm nrm,
+                                                           __half* __restrict__ hi, __half* __restrict__ lo,
+                                                           int H, int W, int Ha, int Wb) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Ha * Wb) return;
+  const int n = blockIdx.y;
+  const int a = idx / Wb, b = idx - a * Wb;
+  const int64_t src_n = gather_idx ? gather_idx[n] : n;
+  const uint8_t* xn = x + src_n * 3 * (int64_t)H * W;
+  const int row0 = 2 * (a - 2), col0 = 2 * (b - 2);
+  float v[12];                                       // element (dr*2 + dc)*3 + c; 0 outside the image (zero padding
+#pragma unroll                                       // applies to the NORMALISED image, as in the reference)
+  for (int dr = 0; dr < 2; ++dr) {
+    const int row = row0 + dr;
+#pragma unroll
+    for (int dc = 0; dc < 2; ++dc) {
+      const int col = col0 + dc;
+      const bool ok = row >= 0 && row < H && col >= 0 && col < W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float val = 0.f;
+        if (ok) {
+          const float px = (float)__ldg(xn + ((int64_t)row * W + col) * 3 + c);
+          val = __fdiv_rn(__fsub_rn(__fdiv_rn(px, 255.f), nrm.mean[c]), nrm.std[c]);
+        }
+        v[(dr * 2 + dc) * 3 + c] = val;
+      }
+    }
+  }
+  h16x8 oh[2], ol[2];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) split_f16(e < 12 ? v[e] : 0.f, oh[e >> 3].v[e & 7], ol[e >> 3].v[e & 7]);
+  const int64_t base = (((int64_t)n * Ha + a) * Wb + b) * 16;
+  h16x8* dh = reinterpret_cast<h16x8*>(hi + base);
+  dh[0] = oh[0], dh[1] = oh[1];
+  if (lo) {
+    h16x8* dl = reinterpret_cast<h16x8*>(lo + base);
+    dl[0] = ol[0], dl[1] = ol[1];
+  }
+}
+
+int stem_pack_u8_launch(const uint8_t* x, const int64_t* gather_idx, const float* mean3, const float* std3, __half* hi,
+                        __half* lo, int N, int H, int W, int Ha, int Wb, cudaStream_t stream) {
+  if (N == 0) return VB_OK;
+  VB_REQUIRE(N <= 65535, "stem_pack_u8: batch %d too large", N);
+  StemNorm nrm;
+  for (int c = 0; c < 3; ++c) {
+    VB_REQUIRE(std3[c] != 0.f, "stem_pack_u8: std[%d] is zero", c);
+    nrm.mean[c] = mean3[c], nrm.std[c] = std3[c];
+  }
+  dim3 grid((Ha * Wb + 255) / 256, N);
+  stem_pack_u8_kernel<<<grid, 256, 0, stream>>>(x, gather_idx, nrm, hi, lo, H, W, Ha, Wb);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB_OK;
+}
+
 int stem_pack_launch(const float* x, const int64_t* gather_idx, __half* hi, __half* lo, int N, int H,
                      int W, int Ha, int Wb, cudaStream_t stream) {
   if (N == 0) return VB_OK;

@@ -51,6 +51,10 @@ int bn_eval_coef_launch(const float* gamma, const float* beta, const float* rm, 
 int stem_pack_launch(const float* x, const int64_t* gather_idx, __half* hi, __half* lo, int N, int H,
                      int W, int Ha, int Wb, cudaStream_t stream);
 
+// same packing from uint8 HWC frames [N,H,W,3] with ((x/255) - mean[c]) / std[c] fused in (mean3 / std3: host arrays)
+int stem_pack_u8_launch(const uint8_t* x, const int64_t* gather_idx, const float* mean3, const float* std3, __half* hi,
+                        __half* lo, int N, int H, int W, int Ha, int Wb, cudaStream_t stream);
+
 struct WeightPrepEntry {   // one per weight tensor; lives in device memory
   const float* src;        // OIHW fp32 (Linear: [Cout, Cin] with R=S=1)
   int64_t dst_off;         // element offset into the hi / lo planes

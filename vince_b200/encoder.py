@@ -174,6 +174,7 @@ class EncoderRunner:
         self.stats_total = off
         self.bank = WeightBank(specs, passes)
         self.launches = 0          # kernels launched by the last forward (bench bookkeeping)
+        self.input_mean, self.input_std = ops.IMAGENET_MEAN, ops.IMAGENET_STD     # used for uint8 HWC inputs only
         self._plans = {}
         self.block_n_override = None
         import os
@@ -185,6 +186,7 @@ class EncoderRunner:
         import copy
         new = EncoderRunner(copy.deepcopy(self.model, memo), self.passes)
         new.block_n_override = self.block_n_override
+        new.input_mean, new.input_std = self.input_mean, self.input_std
         return new
 
     # ------------------------------------------------------------------------------------------
@@ -300,14 +302,23 @@ class EncoderRunner:
 
     # ------------------------------------------------------------------------------------------
     def forward(self, x, train, gather_idx=None, scatter_idx=None, want_spatial=True):
-        """x: [N,3,H,W] fp32 CUDA.  Returns (spatial NCHW [N,C,h,w] or None, pooled [N,C])."""
+        """x: [N,3,H,W] fp32 CUDA (the reference's normalised frames), or [N,H,W,3] uint8 CUDA (raw HWC frames: the
+        ToTensor(scale=255) + Normalize(self.input_mean, self.input_std) of utils/transforms.py:89-101 is then fused
+        into the stem packing).  Returns (spatial NCHW [N,C,h,w] or None, pooled [N,C])."""
         if not x.is_cuda:
             raise RuntimeError("vince_b200 encoder: input must be a CUDA tensor (no CPU fallback)")
-        if x.dtype != torch.float32:
-            raise TypeError("vince_b200 encoder: input must be fp32 (the reference's arithmetic type)")
+        raw_u8 = x.dtype == torch.uint8
+        if raw_u8:
+            if x.dim() != 4 or x.shape[-1] != 3:
+                raise ValueError("vince_b200 encoder: uint8 input must be HWC frames [N,H,W,3]")
+        elif x.dtype != torch.float32:
+            raise TypeError("vince_b200 encoder: input must be fp32 NCHW (the reference's arithmetic type) or uint8 NHWC")
         x = x.contiguous()
         dev = x.device
-        N, C3, H, W = x.shape
+        if raw_u8:
+            N, H, W, C3 = x.shape
+        else:
+            N, C3, H, W = x.shape
         with torch.cuda.device(dev):
             self.bank.refresh()
             key = (N, H, W, bool(train), dev.index, self.bank.generation)
@@ -328,7 +339,10 @@ class EncoderRunner:
             if scatter_idx is not None:
                 plan.idx_scatter.copy_(scatter_idx)
                 si = plan.idx_scatter
-            ops.build_stem_pack(x, gi, plan.x_hi, plan.x_lo)()
+            if raw_u8:
+                ops.build_stem_pack_u8(x, gi, plan.x_hi, plan.x_lo, self.input_mean, self.input_std)()
+            else:
+                ops.build_stem_pack(x, gi, plan.x_hi, plan.x_lo)()
             for run in plan.launches:
                 run()
             f = plan.final

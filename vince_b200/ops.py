@@ -156,6 +156,24 @@ def stem_pack(*a):
     build_stem_pack(*a)()
 
 
+IMAGENET_MEAN = (0.485, 0.456, 0.406)      # utils/transforms.py:85,100 (== constants.py:28-29 / 255)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def build_stem_pack_u8(x_nhwc, gather_idx, x_hi, x_lo, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """x_nhwc: [N,H,W,3] uint8 CUDA.  ToTensor(scale=255) + Normalize(mean, std) fused into the packing."""
+    N, H, W, C = x_nhwc.shape
+    if C != 3:
+        raise ValueError("stem_pack_u8: expected HWC frames with 3 channels")
+    m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+    run = _bind(_lib.lib().vince_stem_pack_u8, "vince_stem_pack_u8", _ptr(x_nhwc, torch.uint8, "x"),
+                _ptr(gather_idx, torch.int64, "gather_idx"), m3, s3, _ptr(x_hi, torch.float16, "x_hi"),
+                _ptr(x_lo, torch.float16, "x_lo"), N, H, W)
+    run._keep = (x_nhwc, gather_idx, x_hi, x_lo, m3, s3)
+    return run
+
+
 def build_weight_prep(table_dev, n_entries, max_cout, w_hi, w_lo):
     """max_cout: largest Cout over the table (one block per output channel and tensor)"""
     run = _bind(_lib.lib().vince_weight_prep, "vince_weight_prep", _ptr(table_dev, torch.uint8, "table"), n_entries,

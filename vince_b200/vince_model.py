@@ -308,11 +308,16 @@ class VinceModel(BaseModel):
                 shuffle_order = torch.randperm(n, device=data.device)          # vince_model.py:139
             with torch.cuda.device(data.device):
                 if jigsaw:
+                    if data.dtype == torch.uint8:
+                        raise NotImplementedError("uint8 HWC input is not implemented for the jigsaw branch; pass the "
+                                                  "normalised fp32 NCHW frames")
                     return_val = self._jigsaw_embeddings(data, shuffle_order, jigsaw_orders)
                 else:
-                    # shuffle gather folded into the stem's loads, un-shuffle into the last block's stores
-                    return_val = self.extract_features(data.float() if data.dtype != torch.float32 else data,
-                                                       gather_idx=shuffle_order, scatter_idx=shuffle_order)
+                    # shuffle gather folded into the stem's loads, un-shuffle into the last block's stores; uint8 HWC
+                    # frames go straight to the stem packing kernel, which normalises them (encoder.py)
+                    if data.dtype not in (torch.float32, torch.uint8):
+                        data = data.float()
+                    return_val = self.extract_features(data, gather_idx=shuffle_order, scatter_idx=shuffle_order)
                     head = self._heads["embedding"]
                     head.refresh()
                     hidden = head.linear(0, return_val["extracted_features"], relu=True)
