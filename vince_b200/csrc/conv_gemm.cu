@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
     const int row = quarter * 32 + lane;
     const int etid = threadIdx.x - EPI_TID0;       // 0..127
     const bool store_leader = (etid == 0);
+    const uint32_t staging_s = smem_u32(staging);
     // halo mode: which output pixel (if any) this accumulator row is
     int hy = 0, hx = 0;
     if (HALO) {
@@ -520,12 +521,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
         named_bar_sync(2, 128);
         if (valid) {
           // 128-byte row `srow`, 16-byte chunk j stored at (j ^ (srow & 7)) : SWIZZLE_128B, conflict-free
-          uint8_t* rowp = staging + srow * 128;
+          const uint32_t rowp = staging_s + (uint32_t)srow * 128u;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 f = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            *reinterpret_cast<float4*>(rowp + ((j ^ (srow & 7)) << 4)) = f;
-          }
+          for (int j = 0; j < 8; ++j)
+            sts_v4(rowp + (uint32_t)((j ^ (srow & 7)) << 4), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
@@ -543,28 +542,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
           // small-K 1x1).  The next chunk's first barrier keeps the tile alive until every warp is done.
           const int r_end = min(32, nvalid - quarter * 32);
           float sa = 0.f, sb = 0.f, sc = 0.f, sd = 0.f, qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f;
-          const uint8_t* base = staging + (quarter * 32) * 128 + ((lane & 3) << 2);
+          const uint32_t base = staging_s + (uint32_t)((quarter * 32) * 128 + ((lane & 3) << 2));
           const int cj = lane >> 2;
           if (r_end == 32) {
 #pragma unroll
             for (int r = 0; r < 32; r += 4) {
-              const float x0 = *reinterpret_cast<const float*>(base + (r + 0) * 128 + ((cj ^ ((r + 0) & 7)) << 4));
-              const float x1 = *reinterpret_cast<const float*>(base + (r + 1) * 128 + ((cj ^ ((r + 1) & 7)) << 4));
-              const float x2 = *reinterpret_cast<const float*>(base + (r + 2) * 128 + ((cj ^ ((r + 2) & 7)) << 4));
-              const float x3 = *reinterpret_cast<const float*>(base + (r + 3) * 128 + ((cj ^ ((r + 3) & 7)) << 4));
+              const float x0 = lds_f32(base + (uint32_t)((r + 0) * 128 + ((cj ^ ((r + 0) & 7)) << 4)));
+              const float x1 = lds_f32(base + (uint32_t)((r + 1) * 128 + ((cj ^ ((r + 1) & 7)) << 4)));
+              const float x2 = lds_f32(base + (uint32_t)((r + 2) * 128 + ((cj ^ ((r + 2) & 7)) << 4)));
+              const float x3 = lds_f32(base + (uint32_t)((r + 3) * 128 + ((cj ^ ((r + 3) & 7)) << 4)));
               sa += x0, sb += x1, sc += x2, sd += x3;
               qa = fmaf(x0, x0, qa), qb = fmaf(x1, x1, qb), qc = fmaf(x2, x2, qc), qd = fmaf(x3, x3, qd);
             }
           } else {
             for (int r = 0; r < r_end; ++r) {
-              const float x0 = *reinterpret_cast<const float*>(base + r * 128 + ((cj ^ (r & 7)) << 4));
+              const float x0 = lds_f32(base + (uint32_t)(r * 128 + ((cj ^ (r & 7)) << 4)));
               sa += x0;
               qa = fmaf(x0, x0, qa);
             }
           }
-          double* my = smem_stats + quarter * 2 * BN + chunk * 32 + lane;
-          my[0] += (double)((sa + sb) + (sc + sd));
-          my[BN] += (double)((qa + qb) + (qc + qd));
+          const uint32_t my = smem_u32(smem_stats) + (uint32_t)(quarter * 2 * BN + chunk * 32 + lane) * 8u;
+          sts_f64(my, lds_f64(my) + (double)((sa + sb) + (sc + sd)));
+          sts_f64(my + BN * 8u, lds_f64(my + BN * 8u) + (double)((qa + qb) + (qc + qd)));
         }
       }
     }

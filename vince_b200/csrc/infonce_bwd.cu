@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(NB_THREADS, 1) infonce_bwd_kernel(const __grid
       const bool needs_mask = is_key || (j0 + NB_BN > limit);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
-      const uint8_t* st = stages + (size_t)stage * stage_bytes;
+      const uint32_t st = smem_u32(stages + (size_t)stage * stage_bytes);
 #pragma unroll 1
       for (int chunk = 0; chunk < NB_BN / 32; ++chunk) {
         uint32_t raw[32];
@@ -208,8 +208,7 @@ __global__ void __launch_bounds__(NB_THREADS, 1) infonce_bwd_kernel(const __grid
 #pragma unroll
           for (int d4 = 0; d4 < DH / 4; ++d4) {
             const int d = half * DH + d4 * 4;          // feature index; atom d / 32, 16-byte chunk (d % 32) / 4
-            const uint8_t* src = st + (d >> 5) * (NB_BN * 128) + j * 128 + ((((d & 31) >> 2) ^ (j & 7)) << 4);
-            const float4 n = *reinterpret_cast<const float4*>(src);
+            const float4 n = lds_v4(st + (uint32_t)((d >> 5) * (NB_BN * 128) + j * 128 + ((((d & 31) >> 2) ^ (j & 7)) << 4)));
             acc_d[4 * d4 + 0] = fmaf(pj, n.x, acc_d[4 * d4 + 0]);
             acc_d[4 * d4 + 1] = fmaf(pj, n.y, acc_d[4 * d4 + 1]);
             acc_d[4 * d4 + 2] = fmaf(pj, n.z, acc_d[4 * d4 + 2]);
