@@ -759,6 +759,9 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   const size_t planes = d.passes == 3 ? 2 : 1;
   // CTA pairs (cta_group::2): worthwhile whenever there are at least a few 256-row tiles per SM pair
   int cg = ((d.M + BM - 1) / BM >= 8) ? 2 : 1;
+  // at most 4 k-blocks per tile: the layer is bound by its epilogue / output stream, where the pair's cross-CTA
+  // hand-shakes only cost (stem: 430 -> 399 us measured)
+  if (d.K <= 4 * BK && !(getenv("VINCE_B200_SMALLK_PAIR") && atoi(getenv("VINCE_B200_SMALLK_PAIR")) == 1)) cg = 1;
   {
     const char* e = getenv("VINCE_B200_CTA_PAIR");     // 0 forces single-CTA tiles (debug / A-B comparison)
     if (e && atoi(e) == 0) cg = 1;
