@@ -12,9 +12,11 @@
  *     allocated inside (scratch comes in through `workspace` arguments sized by *_workspace_bytes());
  *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
  *   - activations between convolutions are NHWC, carried as a pair of fp16 planes (hi, lo) with
- *     x ~= hi + lo (|err| <= 2^-17 |x|); with `passes` = 3 each MMA k-step computes hi*hi + lo*hi + hi*lo so
- *     the result matches the reference's fp32 arithmetic to ~1e-5; `passes` = 1 uses the hi plane only
- *     (plain fp16, lo pointers may be NULL).
+ *     hi = fp16(x), lo = fp16(x - hi), x ~= hi + lo (|err| <= 2^-24 |x| while lo is a normal fp16 number;
+ *     conversions saturate at +-65504); with `passes` = 3 each MMA k-step computes hi*hi + lo*hi + hi*lo into an
+ *     fp32 accumulator, so the result matches the reference's fp32 arithmetic to ~1e-6 per layer; `passes` = 1
+ *     uses the hi plane only (plain fp16, lo pointers may be NULL).  Weights are pre-scaled by an exact power of
+ *     two (vince_weight_entry.scale_log2) that vince_conv_desc.alpha undoes.
  */
 #ifndef VINCE_B200_H_
 #define VINCE_B200_H_
