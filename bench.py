@@ -272,7 +272,7 @@ def run_ours(a):
             dist.barrier()
             dist.destroy_process_group()
         if rank == 0:
-            print(json.dumps({"profile_only": True, "ms_per_step_under_profiler": round(ms / a.steps, 3)}))
+            emit({"profile_only": True, "ms_per_step_under_profiler": round(ms / a.steps, 3)})
         return
     # ---- InfoNCE step (similarity+CE+metrics + EMA + enqueue) timed alone, device resident ----
     keys = torch.nn.functional.normalize(torch.randn((wl["B"], wl["D"]), device=dev), dim=1)
@@ -349,7 +349,7 @@ def run_ours(a):
         "gpu_launches": hp.launches * a.steps,
         "gpu_launches_per_step": hp.launches,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -425,10 +425,28 @@ def run_reference(a):
                                    "CPU sample batch=32 frames" % (1 if wl["backbone"] == "ResNet18" else 2, wl["backbone"])},
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(obj):
+    """The ONE JSON line goes to the process's original stdout; everything else printed during the run (NCCL's version
+    banner, library chatter) was re-routed to stderr by main()."""
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)              # C-level and Python-level stdout -> stderr for the rest of the run
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
