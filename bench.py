@@ -111,7 +111,6 @@ class HotPath:
         import torch
 
         import vince_b200
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
         self.torch, self.wl, self.dev, self.world, self.gather = torch, wl, dev, world, gather
         self.args = make_args(dev, wl)
         torch.manual_seed(0)

@@ -66,6 +66,26 @@ def test_ops_reject_cpu_tensors_and_missing_library():
     assert "RAISED True" in out.stdout, out.stdout + out.stderr
 
 
+def test_new_entry_points_validate_on_the_host():
+    """uint8 stem packing, the InfoNCE backward and the prefetcher refuse CPU tensors / devices before any launch."""
+    from vince_b200 import _lib, ops
+    from vince_b200.prefetch import BatchPrefetcher
+    x8 = torch.zeros((2, 8, 8, 3), dtype=torch.uint8)
+    hi = torch.zeros((2, 7, 7, 16), dtype=torch.float16)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.build_stem_pack_u8(x8, None, hi, hi.clone())
+    with pytest.raises(ValueError):
+        ops.build_stem_pack_u8(torch.zeros((2, 8, 8, 4), dtype=torch.uint8), None, hi, hi.clone())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        BatchPrefetcher("cpu")
+    lib = _lib.lib()
+    assert lib.vince_infonce_bwd_workspace_bytes(256, 128) >= 2 * 148 * 128 * 128 * 4
+    d = _lib.InfoNceDesc()
+    d.B, d.Bk, d.K, d.D, d.num_frames, d.temperature = 8, 8, 0, 48, 2, 0.07          # D not a multiple of 32
+    assert lib.vince_infonce_bwd(ctypes.byref(d), 1.0, 0, 0, None, None) < 0
+    assert b"embedding size" in lib.vince_last_error()
+
+
 def test_model_refuses_cpu_inputs_and_cpu_parameters():
     import vince_b200
     args = make_args(batch_size=4, num_frames=2, queue_size=16, embedding_size=32, device="cuda:0")
