@@ -149,8 +149,11 @@ def test_jigsaw_matches_reference_golden(golden):
     x = torch.from_numpy(g[case + "/x"]).to(DEV)
     perm = torch.from_numpy(g[case + "/perm"])
     orders = torch.from_numpy(g[case + "/orders"])
-    with injected_randperm([perm] + list(orders)):
-        r = model.get_embeddings({"data": x, "batch_types": ["images"], "batch_sizes": [B]}, jigsaw=True, shuffle=True)[0]
+    # the reference draws randperm(9) per row on the host (vince_model.py:166); here the per-row orders are one batched
+    # device draw, so the golden orders are handed in explicitly
+    with injected_randperm([perm]):
+        r = model.get_embeddings({"data": x, "batch_types": ["images"], "batch_sizes": [B]}, jigsaw=True, shuffle=True,
+                                 jigsaw_orders=orders)[0]
     torch.cuda.synchronize()
     assert rel(r["embeddings"], g[case + "/embeddings"]) < EMB_TOL
     assert rel(r["prenorm_features"], g[case + "/prenorm_features"]) < EMB_TOL

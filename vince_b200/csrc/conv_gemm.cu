@@ -692,9 +692,8 @@ static int launch_gemm(const GemmKernelParams& kp, size_t smem, int grid, cudaSt
   return VB_OK;
 }
 
-// Tile width policy.  Measured on B200 (profiles/r01_conv_timeline.md): a tcgen05.mma dispatch from shared-memory
-// operands costs ~22 cycles + max(48, N/2) cycles and every k-block adds ~270 cycles of barrier / descriptor work in
-// the single issuing thread, so wider tiles amortise better - unless they leave SMs idle in the last wave.
+// Tile width policy: minimise waves x max(main loop, epilogue) per tile with measured per-MMA / per-k-block / per-chunk
+// costs (profiles/r01_summary.md); wider tiles amortise better unless they leave SMs idle in the last wave.
 static int auto_block_n(const ConvGemmDesc& d, int cg) {
   const int cands[3] = {256, 128, 64};
   const long m_blocks = ((d.M + BM - 1) / BM + cg - 1) / cg;
@@ -712,13 +711,17 @@ static int auto_block_n(const ConvGemmDesc& d, int cg) {
     const long tiles = m_blocks * ((d.N + bn - 1) / bn);
     const long waves = (tiles + units - 1) / units;
     const long passes = d.passes == 3 ? 3 : 1;
-    // issue side: per-MMA dispatch + per-k-block barrier/descriptor overhead; tensor side: bn/2 cycles per MMA per SM
-    const long dispatch = cg == 2 ? 30 + bn / 8 : 22 + (bn / 2 > 48 ? bn / 2 : 48);
-    const long issue = 4 * passes * dispatch + (cg == 2 ? 500 : 270);
-    const long pipe = 4 * passes * (bn / 2 > 48 ? bn / 2 : 48);
-    const long mainloop = (long)(d.K / BK) * (issue > pipe ? issue : pipe);
-    const long epilogue = 900L * (bn / 32);          // overlaps the next tile's main loop (double-buffered TMEM)
+    // per MMA: the tensor pipe needs bn/2 cycles, the issuing thread ~50 (measured with the 32-bit-descriptor issue
+    // loop: N = 64 MMAs retire every ~50 cycles, N >= 128 at the tensor rate); per k-block ~120 cycles of barrier /
+    // commit work.  With these constants the model reproduces the measured preference of 128-wide tiles for layer4
+    // (98 tiles of 256 leave the second wave of 74 CTA pairs two-thirds idle: 158 -> 128 us) and of 256 for layer3.
+    const long per_mma = bn / 2 > 50 ? bn / 2 : 50;
+    const long mainloop = (long)(d.K / BK) * (4 * passes * per_mma + 120);
+    const long epilogue = 1100L * (bn / 32);         // overlaps the next tile's main loop (double-buffered TMEM)
     const long cost = waves * (mainloop > epilogue ? mainloop : epilogue);
+    // at most 4 k-blocks: the layer is bound by its output stream, and every halving of the tile width re-reads the
+    // activations once more - take the widest tile that fits (measured: R50 128->512 161 us at 256 vs 202 us at 128)
+    if (d.K / BK <= 4) return bn;
     if (best_cost < 0 || cost < best_cost) best_cost = cost, best = bn;
   }
   return best;
