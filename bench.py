@@ -44,6 +44,22 @@ def load_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
+def ncu_conv_traffic():
+    """Average DRAM bytes (read + write) per conv_gemm launch from the committed ncu capture of this same command
+    (profiles/r01_step_metrics_all_launches.csv, dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01_step_metrics_all_launches.csv")
+    try:
+        rows = list(csv.reader(open(path, newline="")))
+        hdr = rows[0]
+        k, r, w = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[rows[1][r]]
+        vals = [(float(x[r].replace(",", "")) + float(x[w].replace(",", ""))) * unit for x in rows[2:] if "conv_gemm" in x[k]]
+        return (round(sum(vals) / len(vals)), len(vals)) if vals else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -302,12 +318,17 @@ def run_ours(a):
             dist.destroy_process_group()
         return
     peaks = load_peaks()
+    traffic = ncu_conv_traffic() if wl["backbone"] == "ResNet18" else None
     achieved_tf = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
     peak_tf = peaks["tf_sustained"]
     roofline = {
         "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, fp16x3)", "bound": "tensor",
         "achieved": round(achieved_tf, 2), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(achieved_tf / peak_tf, 4),
-        "traffic": None, "peak_source": "%s bf16 cuBLAS sustained (same tensor rate as fp16; kernel timed inside a long step)" % peaks["source"],
+        "traffic": traffic[0] if traffic else None,
+        "traffic_source": ("bytes per launch: mean dram__bytes_read.sum + dram__bytes_write.sum over the %d conv_gemm "
+                           "launches of one step of the ResNet-18 workload in profiles/r01_step_metrics_all_launches.csv "
+                           "(ncu capture of this command)" % traffic[1]) if traffic else None,
+        "peak_source": "%s bf16 cuBLAS sustained (same tensor rate as fp16; kernel timed inside a long step)" % peaks["source"],
         "launches_timed": n_conv, "avg_launch_us": round(conv_ms * 1e3 / max(n_conv, 1), 2),
         "algorithmic_gflop_per_launch": round(conv_flops / max(n_conv, 1) / 1e9, 3),
         "share_of_step": round(conv_ms / ms, 4),
