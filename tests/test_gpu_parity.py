@@ -437,13 +437,22 @@ def test_encoder_overlap_is_bitwise_equal_to_serial():
         assert torch.equal(a, b)
     for a, b in zip(results[0], results[2]):
         assert torch.equal(a, b)
-    # a fork point recorded for another tensor (or a modified one) must not be used
+    # the fork point is honoured only by the call that immediately follows, for the very tensor it saw, unmodified
     qm(batch, shuffle=False)
+    vm._CALLS[0] += 1
+    assert vm._take_fork(data) is not None
+    qm(batch, shuffle=False)
+    vm._CALLS[0] += 1
     other = {"data": data.clone(), "batch_types": ["images"], "batch_sizes": [8]}
     assert vm._take_fork(other["data"]) is None
     qm(batch, shuffle=False)
     data.add_(0.0)                      # bumps the version counter
+    vm._CALLS[0] += 1
     assert vm._take_fork(data) is None
+    qm(batch, shuffle=False)
+    vm._CALLS[0] += 2                   # some other encoder-level call came in between
+    assert vm._take_fork(data) is None
+    torch.cuda.synchronize()
 
 
 def test_uint8_hwc_input_equals_normalised_fp32_input():

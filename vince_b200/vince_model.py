@@ -39,15 +39,16 @@ def _device_of(t):
 # memory pipe while the other's convolutions own the tensor cores.
 #
 # Safe by construction - nothing asynchronous ever leaks out of an API call: VinceQueueModel.forward only RECORDS a
-# fork event on the caller's stream before launching the key encoder there (as always); the next
-# VinceModel.get_embeddings on the same device, if it is handed the very batch tensor the fork saw (same storage,
-# same version counter), runs the query encoder on a private side stream that waits for the fork event only, and the
+# fork event on the caller's stream before launching the key encoder there (as always); the VinceModel.get_embeddings
+# that IMMEDIATELY follows it (no other encoder-level call in between) on the same device, if it is handed the very
+# batch tensor the fork saw (same storage, same version counter), runs the query encoder on a private side stream that waits for the fork event only, and the
 # caller's stream waits for the side stream before get_embeddings returns.  Everything the caller launches afterwards
 # is therefore ordered after BOTH encoders.  Any other call order simply runs on the caller's stream.
 # Disable with args.vince_b200_overlap_encoders = False or VINCE_B200_OVERLAP=0.
 # ---------------------------------------------------------------------------------------------------------------
-_FORK = {}            # device index -> (event, data_ptr, version) recorded by the last VinceQueueModel.forward
+_FORK = {}            # device index -> (event, data_ptr, version, call number) recorded by VinceQueueModel.forward
 _SIDE_STREAMS = {}    # device index -> torch.cuda.Stream
+_CALLS = [0]          # encoder-level API calls so far: a fork point is honoured only by the very next call
 
 
 def _overlap_enabled(args):
@@ -62,12 +63,12 @@ def _record_fork(inputs):
         return
     ev = torch.cuda.Event()
     ev.record(torch.cuda.current_stream(data.device))
-    _FORK[data.device.index] = (ev, data.data_ptr(), data._version)
+    _FORK[data.device.index] = (ev, data.data_ptr(), data._version, _CALLS[0])
 
 
 def _take_fork(data):
     fork = _FORK.pop(data.device.index, None)
-    if fork is None or fork[1] != data.data_ptr() or fork[2] != data._version:
+    if fork is None or fork[1] != data.data_ptr() or fork[2] != data._version or fork[3] != _CALLS[0] - 1:
         return None
     return fork[0]
 
@@ -286,6 +287,8 @@ class VinceModel(BaseModel):
         if not data.is_cuda:
             raise RuntimeError("vince_b200.VinceModel: input batch must already be on the GPU (the solver's "
                                "prefetch thread does the H2D copy, vince_solver.py:352-355); no CPU fallback")
+        if _may_overlap:
+            _CALLS[0] += 1
         fork = _take_fork(data) if (_may_overlap and _overlap_enabled(self.args)) else None
         if fork is None:
             return self._get_embeddings(inputs, jigsaw, shuffle, jigsaw_orders)
@@ -371,6 +374,7 @@ class VinceModel(BaseModel):
     # ------------------------------------------------------------------------------------------
     def forward(self, inputs: Dict[str, torch.Tensor]):
         """vince_model.py:198-250 (similarities) fused with loss_util.similarity_cross_entropy and get_metrics."""
+        _CALLS[0] += 1
         return_val = copy.copy(inputs)
         if inputs.get("data_source") == "IN":
             raise NotImplementedError("ImageNet decoder branch (--use-imagenet) is outside the hot path")
@@ -588,6 +592,7 @@ class VinceQueueModel(BaseModel):
     def forward(self, inputs, jigsaw=False, shuffle=True, jigsaw_orders=None):
         with torch.no_grad():
             queue_data = inputs["queue_data"]
+            _CALLS[0] += 1
             if _overlap_enabled(self.args):
                 _record_fork(inputs)          # lets the query encoder that follows run beside this one
             sub = {"data": queue_data}
