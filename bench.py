@@ -293,17 +293,21 @@ def run_ours(a):
     keys = torch.nn.functional.normalize(torch.randn((wl["B"], wl["D"]), device=dev), dim=1)
     qv = torch.nn.functional.normalize(torch.randn((wl["B"], wl["D"]), device=dev), dim=1)
 
-    def nce_step():
+    def nce_step(backward=False):
         out = {"embeddings": qv, "extracted_features": qv, "queue_embeddings": keys, "data_source": "synthetic",
                "num_frames": wl["nf"]}
         out.update(hp.queue.dequeue())
         out.update(hp.model(out))
         hp.model.loss(out)
         hp.model.get_metrics(out)
+        if backward:
+            hp.model.embedding_gradients(out)          # d loss / d embeddings (what vince_solver.py:465 needs first)
         hp.qm.vince_update(hp.model, enqueue=(hp.queue, keys, [None] * wl["B"], "synthetic"))
     for _ in range(3):
         nce_step()
+        nce_step(True)
     nce_ms = timed(nce_step, 20) / 20
+    nce_bwd_ms = timed(lambda: nce_step(True), 20) / 20
     # ---- end-to-end leg: host (pinned) inputs, H2D inside the timed region, loss read back every step ----
     hp.run_e2e(3)
     e2e_steps = a.steps
@@ -366,6 +370,7 @@ def run_ours(a):
                               "get_embeddings returns); VINCE_B200_OVERLAP=0 serialises them",
                    "l2_policy": "inputs larger than L2: 2 x 154 MB of fp32 frames + >1 GB of activations per step"},
         "infonce_step_ms": round(nce_ms, 4),
+        "infonce_step_with_dq_backward_ms": round(nce_bwd_ms, 4),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "ms_per_step": round(e2e_ms / e2e_steps, 4),
                 "h2d_bytes_per_step": hp.h2d_bytes_per_step, "d2h_bytes_per_step": 4, "steps": e2e_steps,
