@@ -5,7 +5,7 @@ vince_b200.ops refuses non-CUDA tensors.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VINCE_B200_LIB", os.path.join(_HERE, "csrc", "libvince_b200.so"))

@@ -9,7 +9,6 @@ it drives the sm_100a kernels through `EncoderRunner` (vince_b200/encoder.py).
 The torch.nn modules below are PARAMETER CONTAINERS ONLY (initialisation, state_dict, .to(), train()/eval());
 their own forward() is never used.
 """
-import torch
 from torch import nn
 
 from .encoder import EncoderRunner
