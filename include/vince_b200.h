@@ -106,7 +106,9 @@ int vince_stem_pack_u8(const uint8_t* x_nhwc, const int64_t* gather_idx, const f
                        void* x_hi, void* x_lo, int32_t N, int32_t H, int32_t W, void* stream);
 
 /* ---- weight preparation (multi-tensor): OIHW fp32 -> K-major fp16 (hi, lo) ----------------------------------
- * replaces: nothing in the reference (cuDNN consumes OIHW directly); run after every weight update. */
+ * replaces: nothing in the reference (cuDNN consumes OIHW directly); run after every weight update.
+ * `table_dev` is a DEVICE array of n_entries descriptors; one block per (output channel, tensor), so `max_cout` is the
+ * largest Cout in the table. */
 typedef struct {
   const float* src;       /* [Cout,Cin,R,S] fp32 */
   int64_t dst_off;        /* element offset into w_hi / w_lo */
