@@ -105,6 +105,16 @@ int vince_stem_pack(const float* x, const int64_t* gather_idx, void* x_hi, void*
 int vince_stem_pack_u8(const uint8_t* x_nhwc, const int64_t* gather_idx, const float* mean3, const float* std3,
                        void* x_hi, void* x_lo, int32_t N, int32_t H, int32_t W, void* stream);
 
+/* Jigsaw variants (grid = 3): replace the patchify of vince_model.py:144-155 - pad bottom/right with zeros to a
+ * multiple of 3 (BOTH axes by 3 - dim % 3 when either is not divisible, :145-146), cut 3x3 patches, row-major patch
+ * order, [N,3,H,W] -> [9N,3,PH,PW] - by folding it into the stem's loads: packed image 9n + 3*py + px is patch
+ * (py, px) of frame gather_idx[n]; the 9N patch tensor is never written.  x_hi / x_lo hold 9N packed images of the
+ * PH x PW geometry.  grid = 1 is identical to the plain entry points. */
+int vince_stem_pack_grid(const float* x, const int64_t* gather_idx, void* x_hi, void* x_lo, int32_t N, int32_t H,
+                         int32_t W, int32_t grid, void* stream);
+int vince_stem_pack_u8_grid(const uint8_t* x_nhwc, const int64_t* gather_idx, const float* mean3, const float* std3,
+                            void* x_hi, void* x_lo, int32_t N, int32_t H, int32_t W, int32_t grid, void* stream);
+
 /* ---- weight preparation (multi-tensor): OIHW fp32 -> K-major fp16 (hi, lo) ----------------------------------
  * replaces: nothing in the reference (cuDNN consumes OIHW directly); run after every weight update.
  * `table_dev` is a DEVICE array of n_entries descriptors; one block per (output channel, tensor), so `max_cout` is the
@@ -214,6 +224,12 @@ int vince_comm_init(void** comm_out, const void* unique_id_128, int32_t world, i
 int vince_comm_destroy(void* comm);
 int vince_allgather_enqueue(void* comm, const float* keys, int64_t n_local, int32_t D, float* queue, float* queue_tf32,
                             int64_t K, int64_t tail, float* scratch, void* stream);
+/* same, with the momentum EMA of vince_ema_enqueue applied by the scatter kernel's launch (vince_solver.py:497-499 in
+ * one call: all-gather + enqueue + vince_update) */
+int vince_allgather_enqueue_ema(void* comm, const float* keys, int64_t n_local, int32_t D, float* queue,
+                                float* queue_tf32, int64_t K, int64_t tail, float* scratch,
+                                const vince_ema_chunk* table_dev, int32_t n_chunks, float momentum,
+                                float one_minus_momentum, void* stream);
 
 #ifdef __cplusplus
 }

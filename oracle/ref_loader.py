@@ -1,11 +1,14 @@
 """Import the UNMODIFIED reference (danielgordon10/vince) on CPU.  TEST INFRASTRUCTURE ONLY.
 
-Only usable in the dev container, where the reference is mounted read-only at
-/root/reference; the GPU box has no such path, so nothing under `tests -m gpu`,
-`bench.py` or `__graft_entry__.smoke()` may call this.  It is used by
+In the dev container the reference is mounted read-only at /root/reference; elsewhere (the GPU
+box) the byte copies staged by oracle/build_ref.py under oracle/_ref/reference are used (git-ignored,
+travels with the gpurun snapshot).  It is used by
   * oracle/make_golden.py   - to generate tests/golden/*.npz from the real reference
   * tests/test_oracle_vs_reference.py - to pin oracle/vince_oracle.py to the reference
-    (skipped automatically when /root/reference is absent)
+    (skipped automatically when neither location exists)
+  * bench.py --impl reference / cpu_baseline - the reference's own CPU implementation timed on the
+    host cores (cpu_baseline.kind = "reference")
+Never imported by vince_b200/ or by the `-m gpu` parity tests.
 
 The reference needs two un-installable packages (`dg_util`, `efficientnet_pytorch`);
 oracle/dg_util_shim provides import-level stand-ins.
@@ -15,8 +18,18 @@ import sys
 import types
 import warnings
 
-REFERENCE_ROOT = os.environ.get("VINCE_REFERENCE_ROOT", "/root/reference")
-_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dg_util_shim")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STAGED = os.path.join(_HERE, "_ref", "reference")        # oracle/build_ref.py: byte copies of the hot-path modules
+
+
+def _default_root():
+    if os.path.isfile("/root/reference/models/vince_model.py"):
+        return "/root/reference"
+    return _STAGED
+
+
+REFERENCE_ROOT = os.environ.get("VINCE_REFERENCE_ROOT", _default_root())
+_SHIM = os.path.join(_HERE, "dg_util_shim")
 
 
 def reference_available():

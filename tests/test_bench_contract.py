@@ -12,7 +12,7 @@ from conftest import ROOT
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1",
-                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, out.stdout
@@ -23,7 +23,11 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True
     assert d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"]
     assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == os.cpu_count()
+    # oracle/_ref (the staged, unmodified reference) is present wherever build() ran with /root/reference mounted
+    staged = os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "reference", "models", "vince_model.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if staged or os.path.isdir("/root/reference") else "port")
+    assert d["cpu_baseline"]["cores"] == os.cpu_count() and d["cpu_baseline"]["phases"]
+    assert "configs[2]" in d["config"]["workload"] and "forward-only" in d["config"]["step"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

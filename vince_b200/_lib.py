@@ -49,6 +49,10 @@ SIGNATURES = {
     "vince_stem_pack": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "vince_stem_pack_u8": (c_int32, [c_void_p, c_void_p, POINTER(c_float), POINTER(c_float), c_void_p, c_void_p, c_int32,
                                      c_int32, c_int32, c_void_p]),
+    "vince_stem_pack_grid": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                       c_void_p]),
+    "vince_stem_pack_u8_grid": (c_int32, [c_void_p, c_void_p, POINTER(c_float), POINTER(c_float), c_void_p, c_void_p,
+                                          c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "vince_weight_prep": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
     "vince_bn_eval_coef": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int32, c_void_p]),
     "vince_bn_apply": (c_int32, [POINTER(BnSide), c_int32, c_void_p, c_void_p, POINTER(BnSide), c_int32, c_void_p,
@@ -75,6 +79,8 @@ SIGNATURES = {
     "vince_comm_destroy": (c_int32, [c_void_p]),
     "vince_allgather_enqueue": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_int64,
                                           c_void_p, c_void_p]),
+    "vince_allgather_enqueue_ema": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_int64,
+                                              c_void_p, c_void_p, c_int32, c_float, c_float, c_void_p]),
 }
 
 _dll = None

@@ -62,15 +62,28 @@ int vince_stem_pack(const float* x, const int64_t* gather_idx, void* x_hi, void*
                     void* stream) {
   VB_REQUIRE(x && x_hi, "vince_stem_pack: null pointer");
   VB_REQUIRE(N >= 0 && H > 0 && W > 0, "vince_stem_pack: bad shape N=%d H=%d W=%d", N, H, W);
-  return stem_pack_launch(x, gather_idx, HF(x_hi), HF(x_lo), N, H, W, (H - 1) / 2 + 4, (W - 1) / 2 + 4, S(stream));
+  return stem_pack_launch(x, gather_idx, HF(x_hi), HF(x_lo), N, H, W, 1, S(stream));
+}
+
+int vince_stem_pack_grid(const float* x, const int64_t* gather_idx, void* x_hi, void* x_lo, int32_t N, int32_t H,
+                         int32_t W, int32_t grid, void* stream) {
+  VB_REQUIRE(x && x_hi, "vince_stem_pack_grid: null pointer");
+  VB_REQUIRE(N >= 0 && H > 0 && W > 0, "vince_stem_pack_grid: bad shape N=%d H=%d W=%d", N, H, W);
+  return stem_pack_launch(x, gather_idx, HF(x_hi), HF(x_lo), N, H, W, grid, S(stream));
 }
 
 int vince_stem_pack_u8(const uint8_t* x_nhwc, const int64_t* gather_idx, const float* mean3, const float* std3,
                        void* x_hi, void* x_lo, int32_t N, int32_t H, int32_t W, void* stream) {
   VB_REQUIRE(x_nhwc && x_hi && mean3 && std3, "vince_stem_pack_u8: null pointer");
   VB_REQUIRE(N >= 0 && H > 0 && W > 0, "vince_stem_pack_u8: bad shape N=%d H=%d W=%d", N, H, W);
-  return stem_pack_u8_launch(x_nhwc, gather_idx, mean3, std3, HF(x_hi), HF(x_lo), N, H, W, (H - 1) / 2 + 4,
-                             (W - 1) / 2 + 4, S(stream));
+  return stem_pack_u8_launch(x_nhwc, gather_idx, mean3, std3, HF(x_hi), HF(x_lo), N, H, W, 1, S(stream));
+}
+
+int vince_stem_pack_u8_grid(const uint8_t* x_nhwc, const int64_t* gather_idx, const float* mean3, const float* std3,
+                            void* x_hi, void* x_lo, int32_t N, int32_t H, int32_t W, int32_t grid, void* stream) {
+  VB_REQUIRE(x_nhwc && x_hi && mean3 && std3, "vince_stem_pack_u8_grid: null pointer");
+  VB_REQUIRE(N >= 0 && H > 0 && W > 0, "vince_stem_pack_u8_grid: bad shape N=%d H=%d W=%d", N, H, W);
+  return stem_pack_u8_launch(x_nhwc, gather_idx, mean3, std3, HF(x_hi), HF(x_lo), N, H, W, grid, S(stream));
 }
 
 int vince_weight_prep(const vince_weight_entry* table_dev, int32_t n_entries, int64_t max_cout, void* w_hi, void* w_lo,
@@ -132,7 +145,9 @@ int vince_l2_normalize(const float* x, float* out, int32_t rows, int32_t D, floa
 int vince_jigsaw_patchify(const float* x, const int64_t* gather_idx, float* out, int32_t N, int32_t C, int32_t H,
                           int32_t W, void* stream) {
   VB_REQUIRE(N == 0 || (x && out), "vince_jigsaw_patchify: null pointer");
-  const int Hp = (H % 3) ? H + 3 - H % 3 : H, Wp = (W % 3) ? W + 3 - W % 3 : W;
+  // vince_model.py:145-146: BOTH axes grow by 3 - dim % 3 when EITHER is not a multiple of 3
+  const bool pad = (H % 3) != 0 || (W % 3) != 0;
+  const int Hp = pad ? H + 3 - H % 3 : H, Wp = pad ? W + 3 - W % 3 : W;
   return jigsaw_patchify_launch(x, gather_idx, out, N, C, H, W, Hp / 3, Wp / 3, S(stream));
 }
 int vince_jigsaw_gather(const float* in, const int64_t* order, float* out, int32_t N, int32_t C, void* stream) {
@@ -269,12 +284,15 @@ int vince_comm_destroy(void* comm) {
   return VB_OK;
 }
 
-int vince_allgather_enqueue(void* comm, const float* keys, int64_t n_local, int32_t D, float* queue, float* queue_tf32,
-                            int64_t K, int64_t tail, float* scratch, void* stream) {
+static int allgather_enqueue_impl(void* comm, const float* keys, int64_t n_local, int32_t D, float* queue,
+                                  float* queue_tf32, int64_t K, int64_t tail, float* scratch,
+                                  const vince_ema_chunk* table_dev, int32_t n_chunks, float momentum, float one_minus,
+                                  void* stream) {
   VB_REQUIRE(comm && keys && queue && scratch, "vince_allgather_enqueue: null pointer");
   VB_REQUIRE(D > 0 && D % 4 == 0, "vince_allgather_enqueue: D=%d must be a positive multiple of 4", D);
   VB_REQUIRE(K > 0 && tail >= 0 && tail <= K, "vince_allgather_enqueue: bad tail %lld for K=%lld", (long long)tail,
              (long long)K);
+  VB_REQUIRE(n_chunks == 0 || table_dev, "vince_allgather_enqueue: null EMA table");
   int rc = load_nccl();
   if (rc) return rc;
   int world = 0;
@@ -287,14 +305,29 @@ int vince_allgather_enqueue(void* comm, const float* keys, int64_t n_local, int3
   const int64_t total_rows = n_local * world;
   VB_REQUIRE(total_rows <= K, "vince_allgather_enqueue: gathered batch (%lld rows) exceeds the queue (%lld)",
              (long long)total_rows, (long long)K);
-  // rank-ordered gather (ncclFloat32 == 7), then one kernel scatters into the ring (two slices on wrap-around)
+  // rank-ordered gather (ncclFloat32 == 7), then ONE kernel scatters into the ring (two slices on wrap-around) and,
+  // when a table is given, applies the momentum EMA in the same launch
   VB_CHECK_NCCL(g_nccl.AllGather(keys, scratch, (size_t)(n_local * D), 7, reinterpret_cast<ncclComm_t>(comm), S(stream)));
   int64_t t = tail;
   if (t + total_rows > K && t == K) t = 0;   // storage_queue.py:35-43 with an empty head slice
   const int64_t first = (t + total_rows > K) ? (K - t) : total_rows;
   const int64_t second = total_rows - first;
-  return ema_enqueue_launch(nullptr, 0, 0.f, 1.f, queue, queue_tf32, scratch, first * D, t * D, second * D, 0,
-                            first * D, S(stream));
+  return ema_enqueue_launch(reinterpret_cast<const EmaChunk*>(table_dev), n_chunks, momentum, one_minus, queue,
+                            queue_tf32, scratch, first * D, t * D, second * D, 0, first * D, S(stream));
+}
+
+int vince_allgather_enqueue(void* comm, const float* keys, int64_t n_local, int32_t D, float* queue, float* queue_tf32,
+                            int64_t K, int64_t tail, float* scratch, void* stream) {
+  return allgather_enqueue_impl(comm, keys, n_local, D, queue, queue_tf32, K, tail, scratch, nullptr, 0, 0.f, 1.f,
+                                stream);
+}
+
+int vince_allgather_enqueue_ema(void* comm, const float* keys, int64_t n_local, int32_t D, float* queue,
+                                float* queue_tf32, int64_t K, int64_t tail, float* scratch,
+                                const vince_ema_chunk* table_dev, int32_t n_chunks, float momentum,
+                                float one_minus_momentum, void* stream) {
+  return allgather_enqueue_impl(comm, keys, n_local, D, queue, queue_tf32, K, tail, scratch, table_dev, n_chunks,
+                                momentum, one_minus_momentum, stream);
 }
 
 }  // extern "C"

@@ -646,15 +646,21 @@ int bn_eval_coef_launch(const float* gamma, const float* beta, const float* rm, 
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
-static int g_num_sms = 0;
+// per-device caches: one process may drive several GPUs (feature_extractor_gpu_ids[0] != model device, 2-GPU tests)
+constexpr int MAX_DEVICES = 64;
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < MAX_DEVICES) ? dev : 0;
+}
 static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  static int sms[MAX_DEVICES] = {0};
+  const int dev = current_device();
+  if (sms[dev] == 0) {
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sms[dev] <= 0) sms[dev] = 148;
   }
-  return g_num_sms;
+  return sms[dev];
 }
 
 static size_t fixed_smem(int bn) {
@@ -663,11 +669,12 @@ static size_t fixed_smem(int bn) {
 
 template <int BN, int CG, bool HALO, bool RES>
 static int launch_gemm(const GemmKernelParams& kp, size_t smem, int grid, cudaStream_t stream) {
-  static size_t smem_set = 0;                        // per instantiation: the opt-in only ever needs to grow
-  if (smem > smem_set) {
+  static bool smem_set[MAX_DEVICES] = {false};       // per instantiation AND device (the attribute is per context)
+  const int dev = current_device();
+  if (!smem_set[dev]) {
     VB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, CG, HALO, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)SMEM_BUDGET));
-    smem_set = SMEM_BUDGET;
+    smem_set[dev] = true;
   }
   if (CG == 1) {
     conv_gemm_kernel<BN, CG, HALO, RES><<<grid, GEMM_THREADS, smem, stream>>>(kp);

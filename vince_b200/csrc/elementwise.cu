@@ -40,36 +40,48 @@ __device__ __forceinline__ float4 join4(const h16x4& hi, const h16x4& lo) {
 // threads read consecutive column pairs, so every image element is fetched exactly once, coalesced) and four
 // 16-byte stores.  Odd image widths (jigsaw patches, 225^2) take the scalar-load path (rows are then not 8-byte aligned).
 // ------------------------------------------------------------------------------------------------
+// Jigsaw (vince_model.py:144-155): with `grid` = 3 the N source images are read as 9N patches of PH x PW (patch order
+// row-major, image n' = 9 n + py*3 + px starts at source pixel (py*PH, px*PW)); source pixels beyond H x W are the
+// reference's zero padding to a multiple of 3.  Patchify is thereby folded into the stem's loads (the 9N patch tensor
+// is never written).  grid = 1: PH = H, PW = W, plain frames.
+struct StemSrc {
+  int H, W;              // source image size
+  int PH, PW;            // logical (patch) image size
+  int grid;              // 1 or 3
+};
 template <bool EVEN_W>
 __global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ x,
                                                         const int64_t* __restrict__ gather_idx,
                                                         __half* __restrict__ hi, __half* __restrict__ lo,
-                                                        int H, int W, int Ha, int Wb) {
+                                                        StemSrc g, int Ha, int Wb) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Ha * Wb) return;
   const int n = blockIdx.y;
   const int a = idx / Wb, b = idx - a * Wb;
-  const int64_t src_n = gather_idx ? gather_idx[n] : n;
-  const float* xn = x + src_n * 3 * (int64_t)H * W;
+  const int g2 = g.grid * g.grid;
+  const int img = n / g2, patch = n - img * g2;
+  const int roff = (patch / g.grid) * g.PH, coff = (patch % g.grid) * g.PW;
+  const int64_t src_n = gather_idx ? gather_idx[img] : img;
+  const float* xn = x + src_n * 3 * (int64_t)g.H * g.W;
   const int row0 = 2 * (a - 2), col0 = 2 * (b - 2);
   float v[12];                                       // element (dr*2 + dc)*3 + c
 #pragma unroll
   for (int dr = 0; dr < 2; ++dr) {
     const int row = row0 + dr;
-    const bool row_ok = row >= 0 && row < H;
+    const bool row_ok = row >= 0 && row < g.PH && row + roff < g.H;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float v0 = 0.f, v1 = 0.f;
       if (row_ok) {
-        const float* rp = xn + ((int64_t)c * H + row) * W;
+        const float* rp = xn + ((int64_t)c * g.H + row + roff) * g.W + coff;
         if (EVEN_W) {
-          if (col0 >= 0 && col0 < W) {               // W even, col0 even: both columns are inside or both outside
+          if (col0 >= 0 && col0 < g.PW) {            // W even, col0 even: both columns are inside or both outside
             const float2 t = __ldg(reinterpret_cast<const float2*>(rp + col0));
             v0 = t.x, v1 = t.y;
           }
         } else {
-          if (col0 >= 0 && col0 < W) v0 = __ldg(rp + col0);
-          if (col0 + 1 >= 0 && col0 + 1 < W) v1 = __ldg(rp + col0 + 1);
+          if (col0 >= 0 && col0 < g.PW && col0 + coff < g.W) v0 = __ldg(rp + col0);
+          if (col0 + 1 >= 0 && col0 + 1 < g.PW && col0 + 1 + coff < g.W) v1 = __ldg(rp + col0 + 1);
         }
       }
       v[(dr * 2 + 0) * 3 + c] = v0;
@@ -97,13 +109,16 @@ struct StemNorm {
 __global__ void __launch_bounds__(256) stem_pack_u8_kernel(const uint8_t* __restrict__ x,
                                                            const int64_t* __restrict__ gather_idx, StemNorm nrm,
                                                            __half* __restrict__ hi, __half* __restrict__ lo,
-                                                           int H, int W, int Ha, int Wb) {
+                                                           StemSrc g, int Ha, int Wb) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Ha * Wb) return;
   const int n = blockIdx.y;
   const int a = idx / Wb, b = idx - a * Wb;
-  const int64_t src_n = gather_idx ? gather_idx[n] : n;
-  const uint8_t* xn = x + src_n * 3 * (int64_t)H * W;
+  const int g2 = g.grid * g.grid;
+  const int img = n / g2, patch = n - img * g2;
+  const int roff = (patch / g.grid) * g.PH, coff = (patch % g.grid) * g.PW;
+  const int64_t src_n = gather_idx ? gather_idx[img] : img;
+  const uint8_t* xn = x + src_n * 3 * (int64_t)g.H * g.W;
   const int row0 = 2 * (a - 2), col0 = 2 * (b - 2);
   float v[12];                                       // element (dr*2 + dc)*3 + c; 0 outside the image (zero padding
 #pragma unroll                                       // applies to the NORMALISED image, as in the reference)
@@ -112,12 +127,12 @@ __global__ void __launch_bounds__(256) stem_pack_u8_kernel(const uint8_t* __rest
 #pragma unroll
     for (int dc = 0; dc < 2; ++dc) {
       const int col = col0 + dc;
-      const bool ok = row >= 0 && row < H && col >= 0 && col < W;
+      const bool ok = row >= 0 && row < g.PH && col >= 0 && col < g.PW && row + roff < g.H && col + coff < g.W;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         float val = 0.f;
         if (ok) {
-          const float px = (float)__ldg(xn + ((int64_t)row * W + col) * 3 + c);
+          const float px = (float)__ldg(xn + ((int64_t)(row + roff) * g.W + col + coff) * 3 + c);
           val = __fdiv_rn(__fsub_rn(__fdiv_rn(px, 255.f), nrm.mean[c]), nrm.std[c]);
         }
         v[(dr * 2 + dc) * 3 + c] = val;
@@ -136,29 +151,51 @@ __global__ void __launch_bounds__(256) stem_pack_u8_kernel(const uint8_t* __rest
   }
 }
 
+static int stem_src(StemSrc& g, int H, int W, int grid, const char* what) {
+  VB_REQUIRE(grid == 1 || grid == 3, "%s: grid must be 1 (frames) or 3 (jigsaw patches), got %d", what, grid);
+  g.H = H, g.W = W, g.grid = grid, g.PH = H, g.PW = W;
+  if (grid == 3) {
+    // vince_model.py:145-146: pad BOTH axes by 3 - dim % 3 when EITHER is not a multiple of 3
+    const bool pad = (H % 3) != 0 || (W % 3) != 0;
+    g.PH = (pad ? H + 3 - H % 3 : H) / 3;
+    g.PW = (pad ? W + 3 - W % 3 : W) / 3;
+  }
+  return VB_OK;
+}
+
 int stem_pack_u8_launch(const uint8_t* x, const int64_t* gather_idx, const float* mean3, const float* std3, __half* hi,
-                        __half* lo, int N, int H, int W, int Ha, int Wb, cudaStream_t stream) {
+                        __half* lo, int N, int H, int W, int grid_p, cudaStream_t stream) {
   if (N == 0) return VB_OK;
-  VB_REQUIRE(N <= 65535, "stem_pack_u8: batch %d too large", N);
+  StemSrc g;
+  int rc = stem_src(g, H, W, grid_p, "stem_pack_u8");
+  if (rc) return rc;
+  const int NP = N * grid_p * grid_p;
+  VB_REQUIRE(NP <= 65535, "stem_pack_u8: batch %d too large", NP);
+  const int Ha = (g.PH - 1) / 2 + 4, Wb = (g.PW - 1) / 2 + 4;
   StemNorm nrm;
   for (int c = 0; c < 3; ++c) {
     VB_REQUIRE(std3[c] != 0.f, "stem_pack_u8: std[%d] is zero", c);
     nrm.mean[c] = mean3[c], nrm.std[c] = std3[c];
   }
-  dim3 grid((Ha * Wb + 255) / 256, N);
-  stem_pack_u8_kernel<<<grid, 256, 0, stream>>>(x, gather_idx, nrm, hi, lo, H, W, Ha, Wb);
+  dim3 grid((Ha * Wb + 255) / 256, NP);
+  stem_pack_u8_kernel<<<grid, 256, 0, stream>>>(x, gather_idx, nrm, hi, lo, g, Ha, Wb);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }
 
 int stem_pack_launch(const float* x, const int64_t* gather_idx, __half* hi, __half* lo, int N, int H,
-                     int W, int Ha, int Wb, cudaStream_t stream) {
+                     int W, int grid_p, cudaStream_t stream) {
   if (N == 0) return VB_OK;
-  VB_REQUIRE(N <= 65535, "stem_pack: batch %d too large", N);
-  dim3 grid((Ha * Wb + 255) / 256, N);
-  const bool even = (W % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
-  if (even) stem_pack_kernel<true><<<grid, 256, 0, stream>>>(x, gather_idx, hi, lo, H, W, Ha, Wb);
-  else stem_pack_kernel<false><<<grid, 256, 0, stream>>>(x, gather_idx, hi, lo, H, W, Ha, Wb);
+  StemSrc g;
+  int rc = stem_src(g, H, W, grid_p, "stem_pack");
+  if (rc) return rc;
+  const int NP = N * grid_p * grid_p;
+  VB_REQUIRE(NP <= 65535, "stem_pack: batch %d too large", NP);
+  const int Ha = (g.PH - 1) / 2 + 4, Wb = (g.PW - 1) / 2 + 4;
+  dim3 grid((Ha * Wb + 255) / 256, NP);
+  const bool even = grid_p == 1 && (W % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
+  if (even) stem_pack_kernel<true><<<grid, 256, 0, stream>>>(x, gather_idx, hi, lo, g, Ha, Wb);
+  else stem_pack_kernel<false><<<grid, 256, 0, stream>>>(x, gather_idx, hi, lo, g, Ha, Wb);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }

@@ -48,12 +48,14 @@ int bn_eval_coef_launch(const float* gamma, const float* beta, const float* rm, 
 //   X[n,a,b,(dr*2+dc)*3 + c] = x[idx[n], c, 2(a-2)+dr, 2(b-2)+dc]   (0 outside the image, 0 for e >= 12)
 // so that the 7x7/2 pad-3 stem conv becomes a 4x1 stride-1 im2col conv over row pairs with 64-element pixels read
 // at a pixel stride of 16 elements.
+// `grid` = 1: N frames of H x W.  `grid` = 3: the jigsaw branch - the N frames are read as 9N patches (patchify of
+// vince_model.py:144-155 folded into the stem's loads, zero padding to a multiple of 3 included).
 int stem_pack_launch(const float* x, const int64_t* gather_idx, __half* hi, __half* lo, int N, int H,
-                     int W, int Ha, int Wb, cudaStream_t stream);
+                     int W, int grid, cudaStream_t stream);
 
 // same packing from uint8 HWC frames [N,H,W,3] with ((x/255) - mean[c]) / std[c] fused in (mean3 / std3: host arrays)
 int stem_pack_u8_launch(const uint8_t* x, const int64_t* gather_idx, const float* mean3, const float* std3, __half* hi,
-                        __half* lo, int N, int H, int W, int Ha, int Wb, cudaStream_t stream);
+                        __half* lo, int N, int H, int W, int grid, cudaStream_t stream);
 
 struct WeightPrepEntry {   // one per weight tensor; lives in device memory
   const float* src;        // OIHW fp32 (Linear: [Cout, Cin] with R=S=1)

@@ -59,18 +59,24 @@ class KeyGather:
         with torch.cuda.device(self.device):
             _lib.check(lib.vince_comm_init(ctypes.byref(self.comm), raw, self.world, self.rank), "vince_comm_init")
 
-    def enqueue(self, queue, keys, item_images=None, data_source=None):
-        """queue: vince_b200.StorageQueue; keys: [n_local, D] fp32 CUDA.  Every rank ends with identical queues."""
+    def enqueue(self, queue, keys, item_images=None, data_source=None, ema=None):
+        """queue: vince_b200.StorageQueue; keys: [n_local, D] fp32 CUDA.  Every rank ends with identical queues.
+        ema=(table_dev, n_chunks, momentum): also apply the momentum EMA in the scatter kernel's launch."""
         n_local, D = keys.shape
         total = n_local * self.world
         if self._scratch is None or self._scratch.numel() < total * D:
             self._scratch = torch.empty((total * D,), device=self.device, dtype=torch.float32)
+        if queue._shadow_is_stale():
+            queue._refresh_shadow()
+        table, n_chunks, momentum = ema if ema is not None else (None, 0, 0.0)
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().vince_allgather_enqueue(
+            _lib.check(_lib.lib().vince_allgather_enqueue_ema(
                 self.comm, ops._ptr(keys.detach().contiguous(), torch.float32, "keys"), n_local, D,
                 ops._ptr(queue.vector_queue, torch.float32, "queue"),
                 ops._ptr(queue.vector_queue_tf32, torch.float32, "queue_tf32"), queue.maxsize, queue.current_tail,
-                ops._ptr(self._scratch, torch.float32, "scratch"), ops._stream()), "vince_allgather_enqueue")
+                ops._ptr(self._scratch, torch.float32, "scratch"),
+                ops._ptr(table, torch.uint8, "ema table") if n_chunks else None, n_chunks, float(momentum),
+                float(1 - momentum), ops._stream()), "vince_allgather_enqueue_ema")
         images = item_images if item_images is not None else [None] * total
         queue.bookkeep(total, images, data_source)
 

@@ -301,10 +301,12 @@ class EncoderRunner:
         return plan
 
     # ------------------------------------------------------------------------------------------
-    def forward(self, x, train, gather_idx=None, scatter_idx=None, want_spatial=True):
+    def forward(self, x, train, gather_idx=None, scatter_idx=None, want_spatial=True, patch_grid=1):
         """x: [N,3,H,W] fp32 CUDA (the reference's normalised frames), or [N,H,W,3] uint8 CUDA (raw HWC frames: the
         ToTensor(scale=255) + Normalize(self.input_mean, self.input_std) of utils/transforms.py:89-101 is then fused
-        into the stem packing).  Returns (spatial NCHW [N,C,h,w] or None, pooled [N,C])."""
+        into the stem packing).  patch_grid=3 runs the trunk over the 9N jigsaw patches of the N frames
+        (vince_model.py:144-155; the patchify is folded into the stem packing).
+        Returns (spatial NCHW [N,C,h,w] or None, pooled [N,C]) with N -> 9N when patch_grid == 3."""
         if not x.is_cuda:
             raise RuntimeError("vince_b200 encoder: input must be a CUDA tensor (no CPU fallback)")
         raw_u8 = x.dtype == torch.uint8
@@ -319,6 +321,13 @@ class EncoderRunner:
             N, H, W, C3 = x.shape
         else:
             N, C3, H, W = x.shape
+        if patch_grid not in (1, 3):
+            raise ValueError("patch_grid must be 1 or 3")
+        if patch_grid == 3:
+            H, W = ops.jigsaw_patch_size(H, W)
+            N = 9 * N
+            if gather_idx is not None or scatter_idx is not None:
+                raise ValueError("the jigsaw patch path keeps frames in place (no gather / scatter index)")
         with torch.cuda.device(dev):
             self.bank.refresh()
             key = (N, H, W, bool(train), dev.index, self.bank.generation)
@@ -340,9 +349,9 @@ class EncoderRunner:
                 plan.idx_scatter.copy_(scatter_idx)
                 si = plan.idx_scatter
             if raw_u8:
-                ops.build_stem_pack_u8(x, gi, plan.x_hi, plan.x_lo, self.input_mean, self.input_std)()
+                ops.build_stem_pack_u8(x, gi, plan.x_hi, plan.x_lo, self.input_mean, self.input_std, grid=patch_grid)()
             else:
-                ops.build_stem_pack(x, gi, plan.x_hi, plan.x_lo)()
+                ops.build_stem_pack(x, gi, plan.x_hi, plan.x_lo, grid=patch_grid)()
             for run in plan.launches:
                 run()
             f = plan.final

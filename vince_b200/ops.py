@@ -141,35 +141,44 @@ def stem_geometry(H, W):
                           K_true=147))                  # algorithmic K of the 7x7x3 stem (the packed K is 256)
 
 
-def build_stem_pack(x, gather_idx, x_hi, x_lo):
+def jigsaw_patch_size(H, W):
+    """vince_model.py:145-146: both axes are padded by 3 - dim % 3 when EITHER is not a multiple of 3 (so a divisible
+    axis next to a non-divisible one grows by 3); returns the patch size (PH, PW)."""
+    if H % 3 != 0 or W % 3 != 0:
+        H, W = H + 3 - H % 3, W + 3 - W % 3
+    return H // 3, W // 3
+
+
+def build_stem_pack(x, gather_idx, x_hi, x_lo, grid=1):
+    """grid=3: the N frames are packed as 9N jigsaw patches (patchify folded into the stem's loads)."""
     N, C, H, W = x.shape
     if C != 3:
         raise ValueError("stem_pack: expected 3 input channels")
-    run = _bind(_lib.lib().vince_stem_pack, "vince_stem_pack", _ptr(x, torch.float32, "x"),
+    run = _bind(_lib.lib().vince_stem_pack_grid, "vince_stem_pack_grid", _ptr(x, torch.float32, "x"),
                 _ptr(gather_idx, torch.int64, "gather_idx"), _ptr(x_hi, torch.float16, "x_hi"),
-                _ptr(x_lo, torch.float16, "x_lo"), N, H, W)
+                _ptr(x_lo, torch.float16, "x_lo"), N, H, W, grid)
     run._keep = (x, gather_idx, x_hi, x_lo)
     return run
 
 
-def stem_pack(*a):
-    build_stem_pack(*a)()
+def stem_pack(*a, **k):
+    build_stem_pack(*a, **k)()
 
 
 IMAGENET_MEAN = (0.485, 0.456, 0.406)      # utils/transforms.py:85,100 (== constants.py:28-29 / 255)
 IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
-def build_stem_pack_u8(x_nhwc, gather_idx, x_hi, x_lo, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+def build_stem_pack_u8(x_nhwc, gather_idx, x_hi, x_lo, mean=IMAGENET_MEAN, std=IMAGENET_STD, grid=1):
     """x_nhwc: [N,H,W,3] uint8 CUDA.  ToTensor(scale=255) + Normalize(mean, std) fused into the packing."""
     N, H, W, C = x_nhwc.shape
     if C != 3:
         raise ValueError("stem_pack_u8: expected HWC frames with 3 channels")
     m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
     s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
-    run = _bind(_lib.lib().vince_stem_pack_u8, "vince_stem_pack_u8", _ptr(x_nhwc, torch.uint8, "x"),
+    run = _bind(_lib.lib().vince_stem_pack_u8_grid, "vince_stem_pack_u8_grid", _ptr(x_nhwc, torch.uint8, "x"),
                 _ptr(gather_idx, torch.int64, "gather_idx"), m3, s3, _ptr(x_hi, torch.float16, "x_hi"),
-                _ptr(x_lo, torch.float16, "x_lo"), N, H, W)
+                _ptr(x_lo, torch.float16, "x_lo"), N, H, W, grid)
     run._keep = (x_nhwc, gather_idx, x_hi, x_lo, m3, s3)
     return run
 

@@ -9,7 +9,11 @@ Differences, all additive:
   * the copies are done by the coalesced `vince_ema_enqueue` kernel, which in the same pass maintains
     `vector_queue_tf32`, a copy of the queue rounded (RN) to TF32 that the fused InfoNCE kernel streams through the
     tensor cores; `dequeue()` returns it under the extra key "queue_vectors_tf32";
-  * `enqueue_gathered(gather, items, ...)` enqueues the rank-ordered all-gather of `items` (multi-GPU).
+  * the shadow follows out-of-band writes too: code that assigns `queue.vector_queue = ...` or mutates it with torch
+    ops (`vector_queue.copy_(...)`, checkpoint restore) changes the tensor's identity / version counter, which
+    `dequeue()` notices and answers by re-rounding the shadow;
+  * multi-GPU: `vince_b200.distributed.KeyGather.enqueue(queue, keys, ...)` enqueues the rank-ordered all-gather of
+    every rank's keys.
 """
 import torch
 
@@ -37,12 +41,25 @@ class StorageQueue(object):
             torch.randn((self.maxsize, self.feat_size), device=dev, requires_grad=False, dtype=self.dtype), dim=-1
         ).contiguous()
         self.vector_queue_tf32 = torch.empty_like(self.vector_queue)
-        with torch.cuda.device(dev):
-            ops.round_tf32(self.vector_queue, self.vector_queue_tf32)
+        self._refresh_shadow()
         self.image_queue = [None for _ in range(self.maxsize)]
         self.data_source_queue = [None for _ in range(self.maxsize)]
         self.current_tail = 0
         self.full = False
+
+    def _refresh_shadow(self):
+        vq = self.vector_queue
+        if self.vector_queue_tf32 is None or self.vector_queue_tf32.shape != vq.shape or \
+                self.vector_queue_tf32.device != vq.device:
+            self.vector_queue_tf32 = torch.empty_like(vq)
+        with torch.no_grad(), torch.cuda.device(vq.device):
+            ops.round_tf32(vq.contiguous(), self.vector_queue_tf32)
+        self._shadow_key = (vq.data_ptr(), vq._version)
+
+    def _shadow_is_stale(self):
+        # our own kernels write through raw pointers and never touch the version counter; any torch-level write does
+        vq = self.vector_queue
+        return self._shadow_key != (vq.data_ptr(), vq._version)
 
     def __len__(self):
         return len(self.image_queue)
@@ -52,9 +69,9 @@ class StorageQueue(object):
 
     def load(self, vectors):
         """Overwrite the whole buffer (tests / checkpointing); keeps the TF32 shadow coherent."""
-        with torch.no_grad(), torch.cuda.device(self.vector_queue.device):
+        with torch.no_grad():
             self.vector_queue.copy_(vectors)
-            ops.round_tf32(self.vector_queue, self.vector_queue_tf32)
+        self._refresh_shadow()
 
     def enqueue(self, items, item_images, data_source):
         assert len(items) == len(item_images)
@@ -80,6 +97,8 @@ class StorageQueue(object):
         rows = rows.detach()
         if rows.dtype != torch.float32 or rows.shape[1] != self.feat_size:
             raise ValueError("enqueue: expected fp32 rows of width %d" % self.feat_size)
+        if self._shadow_is_stale():
+            self._refresh_shadow()
         with torch.cuda.device(self.vector_queue.device):
             ops.ema_enqueue(None, 0, 0.0, self.vector_queue, self.vector_queue_tf32, rows.contiguous(), at)
 
@@ -103,6 +122,8 @@ class StorageQueue(object):
             self.current_tail = t + n
 
     def dequeue(self):
+        if self._shadow_is_stale():
+            self._refresh_shadow()
         return {
             "queue_vectors": self.vector_queue.detach(),
             "queue_images": self.image_queue,

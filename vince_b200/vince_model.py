@@ -17,6 +17,8 @@ not built yet); `loss()` returns detached tensors.
 """
 import copy
 import os
+import time
+import warnings
 from typing import Dict, Optional, Tuple
 
 import numpy as np
@@ -92,6 +94,37 @@ def _record_stream_all(obj, stream):
             _record_stream_all(v, stream)
 
 
+TIME_STR = time.strftime("%Y_%m_%d_%H_%M_%S")     # constants.py:23 (one sub-directory per run, as in the reference)
+
+
+def _checkpoint_files(folder):
+    """All *.pt files under `folder` (recursively: the reference saves into checkpoint_dir/TIME_STR) as
+    (iteration, mtime, path); the iteration is the trailing integer of the file name."""
+    found = []
+    for root, _, files in os.walk(folder):
+        for f in files:
+            if not f.endswith(".pt"):
+                continue
+            digits = "".join(ch if ch.isdigit() else " " for ch in os.path.splitext(f)[0]).split()
+            it = int(digits[-1]) if digits else 0
+            path = os.path.join(root, f)
+            found.append((it, os.path.getmtime(path), path))
+    return sorted(found)
+
+
+def save_checkpoint(model, folder, num_to_keep, iteration):
+    """dg_util pytorch_util.save semantics as used at models/base_model.py:23-25: write `folder/<iteration>.pt`
+    (state_dict), then keep only the newest `num_to_keep` files of that folder (num_to_keep < 0 keeps all)."""
+    os.makedirs(folder, exist_ok=True)
+    path = os.path.join(folder, "%010d.pt" % iteration)
+    torch.save(model.state_dict(), path)
+    if num_to_keep > 0:
+        files = sorted(f for f in os.listdir(folder) if f.endswith(".pt"))
+        for f in files[:-num_to_keep]:
+            os.remove(os.path.join(folder, f))
+    return path
+
+
 class BaseModel(nn.Module):
     """Stand-in for dg_util's pt_util.BaseModel + models/base_model.py:8-26 (device bookkeeping, save/restore)."""
 
@@ -110,35 +143,61 @@ class BaseModel(nn.Module):
         super().to(device)
 
     def restore(self, skip_filter=None) -> int:
-        """models/base_model.py:13-19: returns the iteration encoded in the newest checkpoint name (0 if none)."""
+        """models/base_model.py:13-19 -> dg_util restore_from_folder: load the newest checkpoint found under
+        args.checkpoint_dir (searched recursively, so run directories written as checkpoint_dir/TIME_STR/ by `save`
+        - ours or the reference's - are found), renaming keys that start with args.saved_variable_prefix to
+        args.new_variable_prefix and dropping keys for which skip_filter(key) is true.  Returns the iteration encoded
+        in the file name (0 when nothing was restored, with a warning)."""
         if not getattr(self.args, "restore", False):
             return 0
         ckpt_dir = self.args.checkpoint_dir
-        if not os.path.isdir(ckpt_dir):
-            return 0
-        files = sorted(f for f in os.listdir(ckpt_dir) if f.endswith(".pt"))
+        files = _checkpoint_files(ckpt_dir) if os.path.isdir(ckpt_dir) else []
         if not files:
+            warnings.warn("vince_b200 restore: no checkpoint (*.pt) found under %r; starting from iteration 0" % ckpt_dir)
             return 0
-        path = os.path.join(ckpt_dir, files[-1])
+        iteration, _, path = files[-1]
         state = torch.load(path, map_location="cpu")
+        if isinstance(state, dict) and "state_dict" in state and not any(torch.is_tensor(v) for v in state.values()):
+            state = state["state_dict"]
+        old = getattr(self.args, "saved_variable_prefix", None)
+        new = getattr(self.args, "new_variable_prefix", None)
+        if old is not None and new is not None:
+            state = {(new + k[len(old):] if k.startswith(old) else k): v for k, v in state.items()}
         if skip_filter is not None:
             state = {k: v for k, v in state.items() if not skip_filter(k)}
-        self.load_state_dict(state, strict=False)
-        try:
-            return int(os.path.splitext(files[-1])[0].split("_")[-1])
-        except ValueError:
-            return 0
+        result = self.load_state_dict(state, strict=False)
+        if result.missing_keys or result.unexpected_keys:
+            warnings.warn("vince_b200 restore from %s: %d missing keys (e.g. %s), %d unexpected keys (e.g. %s)"
+                          % (path, len(result.missing_keys), result.missing_keys[:3], len(result.unexpected_keys),
+                             result.unexpected_keys[:3]))
+        return iteration
 
     def save(self, iteration, num_to_keep=1):
+        """models/base_model.py:21-26: rolling checkpoints under checkpoint_dir/TIME_STR, plus a never-pruned copy in
+        long_save_checkpoint_dir every long_save_frequency saves."""
         if not getattr(self.args, "save", False):
             return
-        os.makedirs(self.args.checkpoint_dir, exist_ok=True)
-        torch.save(self.state_dict(), os.path.join(self.args.checkpoint_dir, "%s_%010d.pt" % (type(self).__name__, iteration)))
-        files = sorted(f for f in os.listdir(self.args.checkpoint_dir) if f.endswith(".pt"))
-        if num_to_keep > 0:
-            for f in files[:-num_to_keep]:
-                os.remove(os.path.join(self.args.checkpoint_dir, f))
+        save_checkpoint(self, os.path.join(self.args.checkpoint_dir, TIME_STR), num_to_keep, iteration)
+        long_dir = getattr(self.args, "long_save_checkpoint_dir", None)
+        freq = getattr(self.args, "long_save_frequency", 0)
+        if long_dir and freq and self.saves > 0 and self.saves % freq == 0:
+            save_checkpoint(self, long_dir, -1, iteration)
         self.saves += 1
+
+
+class _FusedLoss(torch.autograd.Function):
+    """Gives the fused kernel's loss scalar a grad_fn so that `loss.backward()` (vince_solver.py:463-469) reaches
+    VinceModel._backward instead of dying inside autograd with "element 0 of tensors does not require grad"."""
+
+    @staticmethod
+    def forward(ctx, anchor, value, model, network_outputs, loss_name):
+        ctx.model, ctx.network_outputs, ctx.loss_name = model, network_outputs, loss_name
+        return value.detach().clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ctx.model._backward(ctx.network_outputs, ctx.loss_name, grad_out)
+        return None, None, None, None, None
 
 
 class LazySimilarity:
@@ -269,10 +328,10 @@ class VinceModel(BaseModel):
             num_total += batch_size
         return mini_batch_list
 
-    def extract_features(self, inputs, run_average_layer=True, gather_idx=None, scatter_idx=None):
+    def extract_features(self, inputs, run_average_layer=True, gather_idx=None, scatter_idx=None, patch_grid=1):
         return_val = {}
         spatial, pooled = self.feature_extractor(inputs, gather_idx=gather_idx, scatter_idx=scatter_idx,
-                                                 want_pooled=True)
+                                                 want_pooled=True, patch_grid=patch_grid)
         self.launches += self.feature_extractor.module.runner.launches
         return_val["spatial_features"] = spatial
         if run_average_layer:
@@ -310,16 +369,13 @@ class VinceModel(BaseModel):
             if shuffle:
                 shuffle_order = torch.randperm(n, device=data.device)          # vince_model.py:139
             with torch.cuda.device(data.device):
+                # uint8 HWC frames go straight to the stem packing kernel, which normalises them (encoder.py)
+                if data.dtype not in (torch.float32, torch.uint8):
+                    data = data.float()
                 if jigsaw:
-                    if data.dtype == torch.uint8:
-                        raise NotImplementedError("uint8 HWC input is not implemented for the jigsaw branch; pass the "
-                                                  "normalised fp32 NCHW frames")
                     return_val = self._jigsaw_embeddings(data, shuffle_order, jigsaw_orders)
                 else:
-                    # shuffle gather folded into the stem's loads, un-shuffle into the last block's stores; uint8 HWC
-                    # frames go straight to the stem packing kernel, which normalises them (encoder.py)
-                    if data.dtype not in (torch.float32, torch.uint8):
-                        data = data.float()
+                    # shuffle gather folded into the stem's loads, un-shuffle into the last block's stores
                     return_val = self.extract_features(data, gather_idx=shuffle_order, scatter_idx=shuffle_order)
                     head = self._heads["embedding"]
                     head.refresh()
@@ -338,13 +394,11 @@ class VinceModel(BaseModel):
     def _jigsaw_embeddings(self, data, shuffle_order, jigsaw_orders):
         # vince_model.py:144-173.  On one device the batch shuffle only permutes rows, so instead of gathering the
         # images we keep them in place and move the per-row patch permutations to their un-shuffled rows.
-        N, C, H, W = data.shape
+        # The patchify itself (pad to a multiple of 3 with the :145-146 quirk, cut, row-major patch order) is folded into
+        # the stem packing (vince_stem_pack_grid): the [9N,3,H/3,W/3] patch tensor is never written.
+        N = data.shape[0]
         dev = data.device
-        Hp = H + (3 - H % 3) % 3
-        Wp = W + (3 - W % 3) % 3
-        patches = torch.empty((9 * N, C, Hp // 3, Wp // 3), device=dev, dtype=torch.float32)
-        ops.jigsaw_patchify(data.contiguous(), None, patches)
-        return_val = self.extract_features(patches)
+        return_val = self.extract_features(data, patch_grid=3)
         feats = return_val["extracted_features"]                                 # [9N, C]
         if jigsaw_orders is None:
             # vince_model.py:166 draws randperm(9) per row in a Python loop; argsort of iid uniforms is the same
@@ -450,7 +504,11 @@ class VinceModel(BaseModel):
                     "vince_loss_" + name + "softmax_weights": f["weights"].view(B, 1, nP),
                     "vince_loss_" + name + "softmax_weight": f["scalars"][1],
                 })
-                losses["nce_loss" if key == "main" else "nce_loss_self"] = (1.0, f["scalars"][0])
+                lname = "nce_loss" if key == "main" else "nce_loss_self"
+                value = f["scalars"][0]
+                if torch.is_grad_enabled() and self.training:
+                    value = _FusedLoss.apply(self._grad_anchor(value.device), value, self, network_outputs, lname)
+                losses[lname] = (1.0, value)
         elif "vince_similarities" in network_outputs:
             # caller supplied an explicit similarity matrix: generic masked cross entropy kernel
             similarities = network_outputs["vince_similarities"]
@@ -466,6 +524,25 @@ class VinceModel(BaseModel):
                 network_outputs.update({"vince_loss_self_" + key: val for key, val in sl.items()})
                 losses["nce_loss_self"] = (1.0, sl["dist"])
         return losses
+
+    def _grad_anchor(self, device):
+        # a leaf that requires grad, so autograd records _FusedLoss; NOT a Parameter / buffer (state_dict, SGD and the
+        # EMA see exactly the reference's tensors)
+        a = self.__dict__.get("_anchor")
+        if a is None or a.device != device:
+            a = torch.zeros((), device=device, requires_grad=True)
+            self.__dict__["_anchor"] = a
+        return a
+
+    def _backward(self, network_outputs, loss_name, grad_out):
+        """Called by autograd when the solver runs loss.backward().  The query-encoder backward (conv dgrad / wgrad,
+        BatchNorm backward, projection head) is SURVEY.md 8f rank 1 and is not built: fail loudly and say what
+        exists instead of silently leaving every .grad empty."""
+        raise NotImplementedError(
+            "vince_b200: loss.backward() reached the fused InfoNCE loss (%s), but the query-encoder backward is not "
+            "implemented (SURVEY.md 8f rank 1): this build scores (forward, loss, metrics, EMA, enqueue) and provides "
+            "d loss / d embeddings through VinceModel.embedding_gradients(network_outputs); it cannot train. "
+            "Wrap the scoring step in torch.no_grad() to use the loss value only." % loss_name)
 
     def embedding_gradients(self, network_outputs: Dict, loss_weights: Optional[Dict[str, float]] = None):
         """d(sum of weighted losses)/d(embeddings) [B, D] with the fused backward kernel: the tensor autograd hands to
@@ -542,15 +619,15 @@ class VinceQueueModel(BaseModel):
 
     def _table(self, encoder_model):
         import numpy as np
-        # fast path (every training step): same encoder object and its / our first and last parameters still live
-        # where the cached table says (a device move or re-allocation changes all of them)
+        # fast path (every training step): same encoder object and EVERY parameter of both encoders still lives where
+        # the cached table says (re-allocating a single tensor must not leave the kernel writing through a stale pointer)
         probe = self._ema_probe
         if probe is not None and probe[0] is encoder_model and all(p.data_ptr() == ptr for p, ptr in probe[1]):
             return self._ema_table
         dst = self.queue_network.vince_parameters()
         src = encoder_model.vince_parameters()
         key = tuple(p.data_ptr() for p in dst) + tuple(p.data_ptr() for p in src)
-        self._ema_probe = (encoder_model, [(p, p.data_ptr()) for p in (dst[0], dst[-1], src[0], src[-1])])
+        self._ema_probe = (encoder_model, [(p, p.data_ptr()) for p in dst + src])
         if self._ema_key != key:
             chunks = []
             for d, s in zip(dst, src):
@@ -568,26 +645,35 @@ class VinceQueueModel(BaseModel):
             self._ema_key = key
         return self._ema_table
 
-    def param_update(self, encoder_model: VinceModel, momentum: float, enqueue=None):
+    def param_update(self, encoder_model: VinceModel, momentum: float, enqueue=None, gather=None):
         """vince_model.py:587-592 as ONE launch.  `enqueue=(storage_queue, keys, images, data_source)` additionally
-        performs StorageQueue.enqueue in the same launch (the reference does it just before, vince_solver.py:497)."""
+        performs StorageQueue.enqueue in the same launch (the reference does it just before, vince_solver.py:497);
+        with `gather` (a vince_b200.distributed.KeyGather) the keys of every rank are all-gathered first and the
+        rank-ordered rows are enqueued - NCCL all-gather + one kernel."""
         table, n = self._table(encoder_model)
         dev = table.device
         with torch.no_grad(), torch.cuda.device(dev):
             if enqueue is None:
                 ops.ema_enqueue(table, n, momentum)
+            elif gather is not None:
+                queue, keys, images, source = enqueue
+                gather.enqueue(queue, keys, None, source, ema=(table, n, momentum))
+                self.launches = 2
+                return
             else:
                 queue, keys, images, source = enqueue
                 if keys.shape[0] > queue.maxsize:
                     raise ValueError("fused enqueue: batch larger than the queue")
+                if queue._shadow_is_stale():
+                    queue._refresh_shadow()
                 tail = queue.current_tail
                 ops.ema_enqueue(table, n, momentum, queue.vector_queue, queue.vector_queue_tf32,
                                 keys.detach().contiguous(), tail)
                 queue.bookkeep(keys.shape[0], images, source)
         self.launches = 1
 
-    def vince_update(self, encoder_model, enqueue=None):
-        self.param_update(encoder_model, self.vince_momentum, enqueue=enqueue)
+    def vince_update(self, encoder_model, enqueue=None, gather=None):
+        self.param_update(encoder_model, self.vince_momentum, enqueue=enqueue, gather=gather)
 
     def forward(self, inputs, jigsaw=False, shuffle=True, jigsaw_orders=None):
         with torch.no_grad():
