@@ -80,7 +80,24 @@ typedef struct {
   int64_t a_pixel_stride, a_row_stride, a_img_stride;
   float alpha;            /* accumulators are multiplied by alpha before the epilogue (0 = 1): undoes the exact
                            * power-of-two pre-scale of vince_weight_prep */
+  int32_t stats_only;     /* 1: statistics pass - `stats` (+ the fused finalize) are produced, nothing is stored
+                           * (`out` may be NULL).  First half of the train-mode two-pass scheme for wide 1x1 convolutions:
+                           * pass 1 computes the batch statistics, pass 2 recomputes the GEMM with the apply epilogue,
+                           * so the raw [M,N] fp32 tensor and the separate vince_bn_apply pass never touch HBM */
+  /* "apply" epilogue (ABI v2), selected by out_hi != NULL (then out must be NULL and stats / scale / bias unused):
+   *   planes(out) = relu?( alpha*acc*ep_coef[c] + ep_coef[N+c] + residual )
+   * replaces: nn.BatchNorm2d (eval mode, or train mode with coefficients from a statistics pass) + the residual add
+   * + ReLU of resnet.py:76-92,117-137 folded into the producing convolution; same fp32 operation order as
+   * vince_bn_apply, so both routes give identical bits. */
+  void* out_hi;           /* fp16 [M,N] */
+  void* out_lo;
+  const float* ep_coef;   /* [2][N] (scale, shift) */
+  int32_t res_kind;       /* 0 none, 1 planes (res_hi,res_lo) [M,N], 2 bn(res_raw [M,N] fp32) with res_coef [2][N] */
   int32_t reserved;
+  const void* res_hi;
+  const void* res_lo;
+  const float* res_raw;
+  const float* res_coef;
 } vince_conv_desc;
 int vince_conv_fwd(const vince_conv_desc* desc, void* stream);
 /* eval-mode BatchNorm coefficients from the running statistics: coef[2][C] */

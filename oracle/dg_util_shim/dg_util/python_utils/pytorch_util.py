@@ -27,9 +27,24 @@ def save(model, path, num_to_keep, iteration):
     return None
 
 
+class _SingleDevice(nn.Module):
+    """`.module`-bearing pass-through (same state_dict keys as nn.DataParallel)."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+
 def get_data_parallel(module, gpu_ids):
-    # callers use `.module` (end_task_base_solver.py:154); nn.DataParallel is a pass-through without CUDA
-    return nn.DataParallel(module)
+    # callers use `.module` (end_task_base_solver.py:154).  gpu_ids = ["cpu"] (the CPU arm / golden generation) must
+    # stay on the CPU even on a box with GPUs: nn.DataParallel would move the module to cuda:0 there.
+    ids = [g for g in (gpu_ids or []) if str(g) != "cpu"]
+    if not ids or not torch.cuda.is_available():
+        return _SingleDevice(module)
+    return nn.DataParallel(module, [torch.device(g).index if not isinstance(g, int) else g for g in ids])
 
 
 class RemoveDim(nn.Module):

@@ -448,6 +448,36 @@ def test_encoder_full_size_train_mode_vs_oracle(backbone):
     assert torch.equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("backbone,B,H", [("ResNet50", 16, 96), ("ResNet18", 16, 64), ("ResNet50", 64, 224)])
+def test_fused_epilogue_routes_equal_separate_bn_apply_bitwise(backbone, B, H):
+    """The apply epilogue (BatchNorm scale/shift + residual + ReLU -> fp16 planes inside the convolution) performs the
+    same fp32 operations in the same order as vince_bn_apply on the same accumulators, so (1) the train-mode
+    statistics-pass + recompute-pass route for the wide 1x1 expansions and (2) the eval-mode folded-BatchNorm route must
+    reproduce the raw-output + separate-bn_apply route bit for bit - embeddings AND running statistics."""
+    args, model, sd = build_model(backbone, 4, B, 64, 128, seed=21)
+    runner = model.feature_extractor.module.runner
+    gen = torch.Generator().manual_seed(31)
+    x = torch.randn((B, 3, H, H), generator=gen).to(DEV)
+    snap = {k: v.clone() for k, v in model.state_dict().items()}
+    res = {}
+    for mode, train in (("separate", True), ("fused", True), ("separate", False), ("fused", False)):
+        model.load_state_dict(snap)
+        model.train(train)
+        runner.two_pass = runner.fold_eval = 1 if mode == "fused" else 0
+        out = model.get_embeddings({"data": x})
+        torch.cuda.synchronize()
+        res[(mode, train)] = (out["embeddings"].clone(), out["spatial_features"].clone(),
+                              {k: v.clone() for k, v in model.state_dict().items() if "running" in k})
+    runner.two_pass = runner.fold_eval = 1
+    for train in (True, False):
+        a, b = res[("separate", train)], res[("fused", train)]
+        assert torch.equal(a[0], b[0]), "embeddings differ (train=%s)" % train
+        assert torch.equal(a[1], b[1]), "spatial features differ (train=%s)" % train
+        for k in a[2]:
+            assert torch.equal(a[2][k], b[2][k]), k
+    assert not torch.equal(res[("fused", True)][0], res[("fused", False)][0])
+
+
 def test_cfg4_resnet50_jigsaw_full_size_vs_oracle():
     """BASELINE.json configs[4] encoder side: ResNet-50 + jigsaw head, B=128 frames of 224x224 -> 1152 patches of 75x75
     (225-padded), per-row patch orders and the batch shuffle injected; EMBEDDINGS against the fp32 oracle."""

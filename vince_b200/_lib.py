@@ -23,7 +23,9 @@ class ConvDesc(Structure):
         ("bn_num_batches_tracked", c_void_p), ("bn_coef", c_void_p), ("bn_counter", c_void_p),
         ("bn_momentum", c_float), ("bn_eps", c_float),
         ("a_pixel_stride", c_int64), ("a_row_stride", c_int64), ("a_img_stride", c_int64),
-        ("alpha", c_float), ("reserved", c_int32),
+        ("alpha", c_float), ("stats_only", c_int32),
+        ("out_hi", c_void_p), ("out_lo", c_void_p), ("ep_coef", c_void_p), ("res_kind", c_int32), ("reserved", c_int32),
+        ("res_hi", c_void_p), ("res_lo", c_void_p), ("res_raw", c_void_p), ("res_coef", c_void_p),
     ]
 
 

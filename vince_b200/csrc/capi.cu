@@ -30,7 +30,7 @@ static int check_side(const vince_bn_side* s, const char* what) {
 extern "C" {
 
 const char* vince_last_error(void) { return get_error(); }
-int vince_abi_version(void) { return 1; }
+int vince_abi_version(void) { return 2; }
 
 int vince_conv_fwd(const vince_conv_desc* d, void* stream) {
   VB_REQUIRE(d != nullptr, "vince_conv_fwd: null descriptor");
@@ -48,6 +48,9 @@ int vince_conv_fwd(const vince_conv_desc* d, void* stream) {
   g.bn_coef = d->bn_coef, g.bn_counter = d->bn_counter, g.bn_momentum = d->bn_momentum, g.bn_eps = d->bn_eps;
   g.a_pixel_stride = d->a_pixel_stride, g.a_row_stride = d->a_row_stride, g.a_img_stride = d->a_img_stride;
   g.alpha = d->alpha;
+  g.out_hi = d->out_hi, g.out_lo = d->out_lo, g.ep_coef = d->ep_coef, g.res_kind = d->res_kind;
+  g.res_hi = d->res_hi, g.res_lo = d->res_lo, g.res_raw = d->res_raw, g.res_coef = d->res_coef;
+  g.stats_only = d->stats_only;
   g.trace = getenv("VINCE_B200_TRACE_PTR") ? reinterpret_cast<void*>(strtoull(getenv("VINCE_B200_TRACE_PTR"), nullptr, 0)) : nullptr;
   return conv_gemm_launch(g, S(stream));
 }

@@ -40,6 +40,15 @@ constexpr size_t SMEM_BUDGET = 226 * 1024;    // of 227 KB: leaves the 1 KB syst
 
 struct GemmKernelParams {
   CUtensorMap a_hi, a_lo, b_hi, b_lo, out;
+  CUtensorMap out_hi, out_lo;    // EPI == 1: fp16 (hi, lo) output planes (box 32 channels x 128 rows, SWIZZLE_64B)
+  // EPI == 1 ("apply" epilogue): out = relu?( acc*alpha*coef[c] + coef[N+c] + residual ) split into fp16 planes
+  const float* ep_coef;          // [2][N] per-channel (scale, shift): BatchNorm coefficients
+  int res_kind;                  // 0 none, 1 fp16 planes [M,N], 2 bn(res_raw) with res_coef (downsample branch)
+  const __half* res_hi;
+  const __half* res_lo;
+  const float* res_raw;
+  const float* res_coef;
+  int stats_only;                // EPI == 0: accumulate BatchNorm sums / finalize but store nothing
   int M, N;
   int num_m_blocks, num_n_blocks;
   int a_mode;                    // 0 tiled, 1 im2col, 2 halo
@@ -108,7 +117,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 // RES ("resident weights"): the layer has a single n-block and this CTA's share of the whole [N, K] weight matrix
 // fits in shared memory next to the activation ring, so it is loaded ONCE per CTA; afterwards only activations
 // stream and the issuing thread waits on / commits to one barrier per activation stage instead of one per k-block.
-template <int BN, int CG, bool HALO, bool RES>
+// EPI = 0: raw fp32 output (+ scale / bias / ReLU, + BatchNorm sums and finalize).  EPI = 1: "apply" epilogue - per-channel
+// scale/shift (BatchNorm with known coefficients) + residual + ReLU, written as the fp16 (hi, lo) planes the next
+// convolution consumes: eval-mode BatchNorm folded into the producing convolution (resnet.py:76-92,117-137), and the
+// second pass of the train-mode "statistics pass + recompute pass" scheme for wide 1x1 convolutions.
+template <int BN, int CG, bool HALO, bool RES, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B tiles
@@ -141,7 +154,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a_hi);
     tma_prefetch_desc(&p.b_hi);
-    tma_prefetch_desc(&p.out);
+    if (EPI == 1) {
+      tma_prefetch_desc(&p.out_hi);
+      tma_prefetch_desc(&p.out_lo);
+    } else {
+      tma_prefetch_desc(&p.out);
+    }
     if (planes == 2) {
       tma_prefetch_desc(&p.a_lo);
       tma_prefetch_desc(&p.b_lo);
@@ -460,7 +478,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
         srow = hy * p.W + hx;
         nvalid = min(p.TH, p.H - y0) * p.W;
       }
-      if (p.stats != nullptr && n_blk != cur_n_blk) {
+      if (EPI == 1 && n_blk != cur_n_blk) {
+        // per-channel coefficients of this n-block, cached in the (otherwise unused) statistics area:
+        // [0,BN) scale  [BN,2BN) shift  [2BN,3BN) residual scale  [3BN,4BN) residual shift
+        float* cf = reinterpret_cast<float*>(smem_stats);
+        named_bar_sync(1, 128);                    // readers of the previous n-block's coefficients are done
+        for (int i = etid; i < BN; i += 128) {
+          const int c = n_blk * BN + i;
+          const bool ok = c < p.N;
+          cf[i] = ok ? __ldg(p.ep_coef + c) : 0.f;
+          cf[BN + i] = ok ? __ldg(p.ep_coef + p.N + c) : 0.f;
+          if (p.res_kind == 2) {
+            cf[2 * BN + i] = ok ? __ldg(p.res_coef + c) : 0.f;
+            cf[3 * BN + i] = ok ? __ldg(p.res_coef + p.N + c) : 0.f;
+          }
+        }
+        named_bar_sync(1, 128);
+        cur_n_blk = n_blk;
+      }
+      if (EPI == 0 && p.stats != nullptr && n_blk != cur_n_blk) {
         if (cur_n_blk >= 0) {
           named_bar_sync(1, 128);
           for (int i = etid; i < BN; i += 128) {
@@ -481,11 +517,135 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
         }
         cur_n_blk = n_blk;
       }
+      // EPI == 1: global row of this accumulator row (residual address)
+      long long m_row = 0;
+      bool row_ok = valid;
+      if (EPI == 1) {
+        if (HALO) m_row = ((long long)img * p.H + (y0 + hy)) * p.W + hx;
+        else m_row = (long long)m_blk * BM + row;
+        row_ok = valid && m_row < (long long)p.M;
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       if (etid == 0) VB_TRACE_EVENT(3, local_t);
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        if (EPI == 1) {
+          const int c0 = n_blk * BN + chunk * 32;
+          // residual loads first: their latency hides behind the TMEM load
+          // one register buffer for either residual kind: planes -> rb[0..3] = 32 hi halves, rb[4..7] = 32 lo halves;
+          // raw -> rb[j] = fp32 channels 4j .. 4j+3
+          uint4 rb[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rb[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (p.res_kind == 1) {
+            if (row_ok) {
+              const uint4* ph = reinterpret_cast<const uint4*>(p.res_hi + m_row * p.N + c0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rb[j] = __ldg(ph + j);
+              if (p.res_lo != nullptr) {
+                const uint4* pl = reinterpret_cast<const uint4*>(p.res_lo + m_row * p.N + c0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rb[4 + j] = __ldg(pl + j);
+              }
+            }
+          } else if (p.res_kind == 2) {
+            if (row_ok) {
+              const uint4* pr = reinterpret_cast<const uint4*>(p.res_raw + m_row * p.N + c0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) rb[j] = __ldg(pr + j);
+            }
+          }
+          uint32_t raw[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk * 32, raw);
+          tmem_ld_wait();
+          if (chunk == BN / 32 - 1) {
+            tc_fence_before_sync();
+            if (CG == 2) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(tmem_empty_leader[acc]);
+            } else {
+              mbar_arrive(&tmem_empty[acc]);
+            }
+          }
+          const uint32_t cfs = smem_u32(smem_stats) + (uint32_t)(chunk * 32) * 4u;
+          // the staging tile must have been drained by the previous chunk's TMA store before anybody writes it
+          if (store_leader && store_pending) tma_store_wait_read0();
+          named_bar_sync(2, 128);
+          // two 8 KB tiles (hi | lo) of 64-byte rows; 16-byte chunk j of row `srow` stored at j ^ ((srow >> 1) & 3):
+          // SWIZZLE_64B (address bits [4,5] ^= bits [7,8]), conflict-free.  One 8-channel group at a time keeps the
+          // live registers at raw[32] + residual[32] + a handful.
+          const uint32_t rowp = staging_s + (uint32_t)srow * 64u;
+          const uint32_t sw = (uint32_t)((srow >> 1) & 3);
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const float4 sc = lds_v4(cfs + (2 * g8 + q) * 16), sh = lds_v4(cfs + BN * 4 + (2 * g8 + q) * 16);
+              v[4 * q + 0] = fmaf(__uint_as_float(raw[8 * g8 + 4 * q + 0]) * p.alpha, sc.x, sh.x);
+              v[4 * q + 1] = fmaf(__uint_as_float(raw[8 * g8 + 4 * q + 1]) * p.alpha, sc.y, sh.y);
+              v[4 * q + 2] = fmaf(__uint_as_float(raw[8 * g8 + 4 * q + 2]) * p.alpha, sc.z, sh.z);
+              v[4 * q + 3] = fmaf(__uint_as_float(raw[8 * g8 + 4 * q + 3]) * p.alpha, sc.w, sh.w);
+            }
+            if (p.res_kind == 1) {
+              const uint32_t hw[4] = {rb[g8].x, rb[g8].y, rb[g8].z, rb[g8].w};
+              const uint32_t lw[4] = {rb[4 + g8].x, rb[4 + g8].y, rb[4 + g8].z, rb[4 + g8].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __half2 a = *reinterpret_cast<const __half2*>(&hw[i]), b = *reinterpret_cast<const __half2*>(&lw[i]);
+                v[2 * i] += __low2float(a) + __low2float(b);
+                v[2 * i + 1] += __high2float(a) + __high2float(b);
+              }
+            } else if (p.res_kind == 2) {
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const float4 rsc = lds_v4(cfs + 2 * BN * 4 + (2 * g8 + q) * 16);
+                const float4 rsh = lds_v4(cfs + 3 * BN * 4 + (2 * g8 + q) * 16);
+                const uint4 r4 = rb[2 * g8 + q];
+                v[4 * q + 0] += fmaf(__uint_as_float(r4.x), rsc.x, rsh.x);
+                v[4 * q + 1] += fmaf(__uint_as_float(r4.y), rsc.y, rsh.y);
+                v[4 * q + 2] += fmaf(__uint_as_float(r4.z), rsc.z, rsh.z);
+                v[4 * q + 3] += fmaf(__uint_as_float(r4.w), rsc.w, rsh.w);
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            uint32_t hq[4], lq[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __half h0, l0, h1, l1;
+              split_f16(v[2 * i], h0, l0);
+              split_f16(v[2 * i + 1], h1, l1);
+              const __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+              hq[i] = *reinterpret_cast<const uint32_t*>(&hh);
+              lq[i] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+            if (valid) {
+              const uint32_t off = (uint32_t)((g8 ^ sw) << 4);
+              sts_v4(rowp + off, make_float4(__uint_as_float(hq[0]), __uint_as_float(hq[1]), __uint_as_float(hq[2]),
+                                             __uint_as_float(hq[3])));
+              sts_v4(rowp + 8192u + off, make_float4(__uint_as_float(lq[0]), __uint_as_float(lq[1]),
+                                                     __uint_as_float(lq[2]), __uint_as_float(lq[3])));
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(2, 128);
+          if (store_leader) {
+            if (HALO) {
+              tma_store_4d(&p.out_hi, staging, c0, 0, y0, img);
+              if (planes == 2) tma_store_4d(&p.out_lo, staging + 8192, c0, 0, y0, img);
+            } else {
+              tma_store_2d(&p.out_hi, staging, c0, m_blk * BM);
+              if (planes == 2) tma_store_2d(&p.out_lo, staging + 8192, c0, m_blk * BM);
+            }
+            tma_store_commit();
+          }
+          store_pending = true;
+          continue;
+        }
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk * 32, raw);
         tmem_ld_wait();
@@ -528,12 +688,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
-        if (store_leader) {
-          if (HALO) tma_store_4d(&p.out, staging, c0, 0, y0, img);
-          else tma_store_2d(&p.out, staging, c0, m_blk * BM);
-          tma_store_commit();
+        if (!p.stats_only) {
+          if (store_leader) {
+            if (HALO) tma_store_4d(&p.out, staging, c0, 0, y0, img);
+            else tma_store_2d(&p.out, staging, c0, m_blk * BM);
+            tma_store_commit();
+          }
+          store_pending = true;
         }
-        store_pending = true;
         if (p.stats != nullptr) {
           // BatchNorm sums from the staged tile (the raw accumulators the TMA store is reading): warp w adds up its
           // 32 staging rows of column `lane` (conflict-free 128-byte row reads, four independent chains) into the
@@ -567,7 +729,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
         }
       }
     }
-    if (p.stats != nullptr) {
+    if (EPI == 0 && p.stats != nullptr) {
       if (cur_n_blk >= 0) {
         named_bar_sync(1, 128);
         for (int i = etid; i < BN; i += 128) {
@@ -667,17 +829,17 @@ static size_t fixed_smem(int bn) {
   return 1024 /*align slack*/ + STAGING_BYTES + (4 * MAX_RING + 4) * 8 + 16 + 8 * bn * 8;
 }
 
-template <int BN, int CG, bool HALO, bool RES>
+template <int BN, int CG, bool HALO, bool RES, int EPI>
 static int launch_gemm(const GemmKernelParams& kp, size_t smem, int grid, cudaStream_t stream) {
   static bool smem_set[MAX_DEVICES] = {false};       // per instantiation AND device (the attribute is per context)
   const int dev = current_device();
   if (!smem_set[dev]) {
-    VB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, CG, HALO, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)SMEM_BUDGET));
+    VB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, CG, HALO, RES, EPI>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
     smem_set[dev] = true;
   }
   if (CG == 1) {
-    conv_gemm_kernel<BN, CG, HALO, RES><<<grid, GEMM_THREADS, smem, stream>>>(kp);
+    conv_gemm_kernel<BN, CG, HALO, RES, EPI><<<grid, GEMM_THREADS, smem, stream>>>(kp);
   } else {
     grid &= ~1;
     cudaLaunchConfig_t cfg;
@@ -693,7 +855,7 @@ static int launch_gemm(const GemmKernelParams& kp, size_t smem, int grid, cudaSt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CG, HALO, RES>, kp));
+    VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CG, HALO, RES, EPI>, kp));
   }
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
@@ -761,7 +923,18 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   VB_REQUIRE(d.K % BK == 0, "conv_gemm: K=%d must be a multiple of %d", d.K, BK);
   VB_REQUIRE(d.N % 32 == 0, "conv_gemm: N=%d must be a multiple of 32", d.N);
   VB_REQUIRE(d.passes == 1 || d.passes == 3, "conv_gemm: passes must be 1 or 3");
-  VB_REQUIRE(d.a_hi && d.b_hi && d.out, "conv_gemm: null operand");
+  const bool planes_out = d.out_hi != nullptr;
+  VB_REQUIRE(d.a_hi && d.b_hi && (d.out || planes_out || d.stats_only), "conv_gemm: null operand");
+  VB_REQUIRE(!(planes_out && d.out), "conv_gemm: give either the fp32 output or the fp16 output planes");
+  if (planes_out) {
+    VB_REQUIRE(d.ep_coef, "conv_gemm: the apply epilogue needs per-channel (scale, shift) coefficients");
+    VB_REQUIRE(d.passes == 1 || d.out_lo, "conv_gemm: fp16x3 needs the lo output plane");
+    VB_REQUIRE(!d.stats && !d.scale && !d.bias && !d.stats_only, "conv_gemm: apply epilogue excludes stats / scale / bias");
+    VB_REQUIRE(d.res_kind >= 0 && d.res_kind <= 2, "conv_gemm: res_kind %d", d.res_kind);
+    VB_REQUIRE(d.res_kind != 1 || d.res_hi, "conv_gemm: residual planes null");
+    VB_REQUIRE(d.res_kind != 2 || (d.res_raw && d.res_coef), "conv_gemm: residual raw / coefficients null");
+  }
+  VB_REQUIRE(!d.stats_only || d.stats, "conv_gemm: stats_only without a stats buffer");
   VB_REQUIRE(d.passes == 1 || (d.a_lo && d.b_lo), "conv_gemm: fp16x3 needs lo planes");
   VB_REQUIRE(!(d.stats && (d.bias || d.scale || d.relu)), "conv_gemm: stats are defined on raw accumulators only");
   VB_REQUIRE(!d.bn_coef || (d.stats && d.bn_gamma && d.bn_beta && d.bn_running_mean && d.bn_running_var && d.bn_counter),
@@ -797,6 +970,11 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   kp.bn_coef = d.bn_coef, kp.bn_counter = d.bn_counter, kp.bn_momentum = d.bn_momentum, kp.bn_eps = d.bn_eps;
   kp.bn_count = (double)d.M;
   kp.trace = reinterpret_cast<unsigned long long*>(d.trace);
+  kp.stats_only = d.stats_only;
+  kp.ep_coef = d.ep_coef;
+  kp.res_kind = planes_out ? d.res_kind : 0;
+  kp.res_hi = reinterpret_cast<const __half*>(d.res_hi), kp.res_lo = reinterpret_cast<const __half*>(d.res_lo);
+  kp.res_raw = d.res_raw, kp.res_coef = d.res_coef;
   kp.debug_skip_mma = getenv("VINCE_B200_DEBUG_SKIP_MMA") ? atoi(getenv("VINCE_B200_DEBUG_SKIP_MMA")) : 0;
   kp.a_plane_bytes = BM * 128;
   kp.a_tx_bytes = BM * 128;
@@ -832,9 +1010,20 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
                               th + 2, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }
-    rc = encode_tma_4d_nhwc(&kp.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.out, d.batch, d.H, d.W, d.N, 32, d.W, th,
-                            CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
+    if (planes_out) {
+      rc = encode_tma_4d_nhwc(&kp.out_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.out_hi, d.batch, d.H, d.W, d.N, 32, d.W, th,
+                              CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+      if (d.out_lo) {
+        rc = encode_tma_4d_nhwc(&kp.out_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.out_lo, d.batch, d.H, d.W, d.N, 32, d.W,
+                                th, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+      }
+    } else if (d.out) {
+      rc = encode_tma_4d_nhwc(&kp.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.out, d.batch, d.H, d.W, d.N, 32, d.W, th,
+                              CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
   } else if (d.im2col) {
     const int P = (d.H + d.pad_lo_h + d.pad_hi_h - d.R) / d.stride + 1;
     const int Q = (d.W + d.pad_lo_w + d.pad_hi_w - d.S) / d.stride + 1;
@@ -876,9 +1065,20 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
     if (rc) return rc;
   }
   if (kp.a_mode != 2) {
-    rc = encode_tma_2d(&kp.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.out, d.N, d.M, (uint64_t)d.N * 4, 32, BM,
-                       CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
+    if (planes_out) {
+      rc = encode_tma_2d(&kp.out_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.out_hi, d.N, d.M, (uint64_t)d.N * 2, 32, BM,
+                         CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+      if (d.out_lo) {
+        rc = encode_tma_2d(&kp.out_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.out_lo, d.N, d.M, (uint64_t)d.N * 2, 32, BM,
+                           CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+      }
+    } else if (d.out) {
+      rc = encode_tma_2d(&kp.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.out, d.N, d.M, (uint64_t)d.N * 4, 32, BM,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
   }
 
   // ---- shared-memory budget: A ring + B ring ----
@@ -918,15 +1118,21 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   if (getenv("VINCE_B200_DEBUG_GRID") && atoi(getenv("VINCE_B200_DEBUG_GRID")) < grid) grid = atoi(getenv("VINCE_B200_DEBUG_GRID"));
   const bool halo = kp.a_mode == 2;
   if (cg == 2) grid &= ~1;
-#define VB_LAUNCH(BN_, CG_)                                                              \
-  if (bn == BN_ && cg == CG_) {                                                          \
-    if (halo) return res ? launch_gemm<BN_, CG_, true, true>(kp, smem, grid, stream)     \
-                         : launch_gemm<BN_, CG_, true, false>(kp, smem, grid, stream);   \
-    return res ? launch_gemm<BN_, CG_, false, true>(kp, smem, grid, stream)              \
-               : launch_gemm<BN_, CG_, false, false>(kp, smem, grid, stream);            \
+#define VB_LAUNCH_E(BN_, CG_, EPI_)                                                             \
+  {                                                                                             \
+    if (halo) return res ? launch_gemm<BN_, CG_, true, true, EPI_>(kp, smem, grid, stream)      \
+                         : launch_gemm<BN_, CG_, true, false, EPI_>(kp, smem, grid, stream);    \
+    return res ? launch_gemm<BN_, CG_, false, true, EPI_>(kp, smem, grid, stream)               \
+               : launch_gemm<BN_, CG_, false, false, EPI_>(kp, smem, grid, stream);             \
+  }
+#define VB_LAUNCH(BN_, CG_)                  \
+  if (bn == BN_ && cg == CG_) {              \
+    if (planes_out) VB_LAUNCH_E(BN_, CG_, 1) \
+    VB_LAUNCH_E(BN_, CG_, 0)                 \
   }
   VB_LAUNCH(64, 1) VB_LAUNCH(128, 1) VB_LAUNCH(256, 1) VB_LAUNCH(64, 2) VB_LAUNCH(128, 2) VB_LAUNCH(256, 2)
 #undef VB_LAUNCH
+#undef VB_LAUNCH_E
   VB_REQUIRE(false, "conv_gemm: no kernel for bn=%d cg=%d", bn, cg);
 }
 

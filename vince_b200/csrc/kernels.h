@@ -37,6 +37,19 @@ struct ConvGemmDesc {
   float bn_momentum, bn_eps;
   long long a_pixel_stride, a_row_stride, a_img_stride;   // im2col: element strides (0 = dense NHWC)
   void* trace;                // debug builds (-DVB_TRACE) only: [4][512] uint64 timeline of CTA 0
+  // ---- "apply" epilogue (out_hi != null, out == null): the output is written as the fp16 (hi, lo) planes of
+  //      relu?( alpha*acc*ep_coef[c] + ep_coef[N+c] + residual ), i.e. BatchNorm with known coefficients (+ the residual
+  //      add and ReLU of resnet.py:76-92,117-137) folded into the producing convolution
+  void* out_hi;
+  void* out_lo;
+  const float* ep_coef;       // [2][N] (scale, shift)
+  int res_kind;               // 0 none, 1 fp16 planes (res_hi, res_lo) [M,N], 2 bn(res_raw [M,N] fp32) with res_coef [2][N]
+  const void* res_hi;
+  const void* res_lo;
+  const float* res_raw;
+  const float* res_coef;
+  // ---- statistics-only pass (needs stats): BatchNorm sums (+ finalize) are produced, nothing is stored
+  int stats_only;
 };
 int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream);
 // eval-mode BatchNorm: coef[2][C] = (gamma / sqrt(running_var + eps), beta - running_mean * scale)

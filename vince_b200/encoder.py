@@ -179,6 +179,10 @@ class EncoderRunner:
         self.block_n_override = None
         import os
         self.halo_mode = int(os.environ.get("VINCE_B200_HALO", "-1"))   # -1 auto, 0 off, 1 force (3x3 stride-1 convs)
+        # train mode: statistics pass + recompute pass for the wide 1x1 expansions (0 = always raw + bn_apply)
+        self.two_pass = int(os.environ.get("VINCE_B200_TWOPASS", "1"))
+        # eval mode: BatchNorm(+residual)+ReLU folded into the producing convolution's epilogue (0 = separate bn_apply)
+        self.fold_eval = int(os.environ.get("VINCE_B200_FOLD_EVAL", "1"))
 
     def __deepcopy__(self, memo):
         # plans hold raw device pointers of THIS model's parameters and arenas: a copy (VinceQueueModel deep-copies
@@ -186,6 +190,7 @@ class EncoderRunner:
         import copy
         new = EncoderRunner(copy.deepcopy(self.model, memo), self.passes)
         new.block_n_override = self.block_n_override
+        new.two_pass, new.fold_eval = self.two_pass, self.fold_eval
         new.input_mean, new.input_std = self.input_mean, self.input_std
         return new
 
@@ -206,21 +211,74 @@ class EncoderRunner:
         return dict(stats=work[o:o + 2 * C], bn=spec.bn, coef=work[o + 2 * C:o + 3 * C].view(torch.float32),
                     counter=work[o + 3 * C:o + 3 * C + 1].view(torch.int32))
 
-    def _build_conv(self, arena, act, spec, work, train, launches):
+    def _conv_geom(self, act, spec):
         P = (act.H + 2 * spec.pad - spec.R) // spec.stride + 1
         Q = (act.W + 2 * spec.pad - spec.R) // spec.stride + 1
-        M = act.N * P * Q
-        raw = arena.alloc((M, spec.Cout), torch.float32)
-        w_hi, w_lo = self.bank.planes(spec)
         geom = None
         if not (spec.R == 1 and spec.stride == 1):
             geom = dict(batch=act.N, H=act.H, W=act.W, Cin=act.C, R=spec.R, S=spec.R, stride=spec.stride,
                         pad_lo_h=spec.pad, pad_lo_w=spec.pad, pad_hi_h=spec.pad, pad_hi_w=spec.pad)
+        return P, Q, act.N * P * Q, geom
+
+    def _coef(self, spec, work):
+        o, C = spec.stats_off, spec.Cout
+        return work[o + 2 * C:o + 3 * C].view(torch.float32)
+
+    def _build_conv(self, arena, act, spec, work, train, launches):
+        """raw fp32 conv output (+ train-mode BatchNorm sums / finalize into the plan's work buffer)"""
+        P, Q, M, geom = self._conv_geom(act, spec)
+        raw = arena.alloc((M, spec.Cout), torch.float32)
+        w_hi, w_lo = self.bank.planes(spec)
         launches.append(ops.build_conv_fwd(act.hi, act.lo, w_hi, w_lo, raw, M, spec.Cout, spec.K, passes=self.passes,
                                            geom=geom, block_n=self._block_n(M, spec.Cout), halo_mode=self.halo_mode,
                                            alpha=WEIGHT_ALPHA,
                                            **self._bn_args(spec, work, train)))
         return raw, P, Q
+
+    def _two_pass(self, spec):
+        """Train mode: is conv+BN cheaper as a statistics pass + a recompute pass with the apply epilogue than as
+        raw output + separate BN-apply?  True for the wide 1x1 expansions (Bottleneck conv3, N = 4K): their time is set
+        by the fp32 output stream (HBM writes run at about half the copy bandwidth), not by the tensor core, so
+        recomputing the small-K GEMM is cheaper than writing and re-reading the raw [M,N] tensor."""
+        if self.two_pass == 0:
+            return False
+        return spec.R == 1 and spec.stride == 1 and spec.Cout >= 4 * spec.K and spec.K <= 512
+
+    def _build_conv_planes(self, arena, act, spec, work, train, launches, relu, res_planes=None, res_side=None):
+        """conv + BatchNorm (+ residual) (+ ReLU) -> fp16 planes, through the cheapest available route:
+        eval mode       one launch, BatchNorm folded into the epilogue (coefficients from the running statistics);
+        train, 2-pass   statistics pass (nothing stored) + recompute pass with the apply epilogue;
+        train, default  raw fp32 output with fused statistics, then the streaming vince_bn_apply pass.
+        res_side = (raw, coef): residual = bn(raw) (downsample branch).  Returns (Act planes, P, Q)."""
+        P, Q, M, geom = self._conv_geom(act, spec)
+        w_hi, w_lo = self.bank.planes(spec)
+        C = spec.Cout
+        common = dict(passes=self.passes, geom=geom, block_n=self._block_n(M, C), halo_mode=self.halo_mode,
+                      alpha=WEIGHT_ALPHA)
+        fused = (not train and self.fold_eval) or (train and self._two_pass(spec))
+        if not fused:
+            raw, P, Q = self._build_conv(arena, act, spec, work, train, launches)
+            hi, lo = self._planes(arena, M, C)
+            kw = {}
+            if res_planes is not None:
+                kw["res_planes"] = res_planes
+            elif res_side is not None:
+                kw["res_bn"] = ops.bn_side(*res_side)
+            launches.append(ops.build_bn_apply(self._side(raw, spec, work), M, C, relu, hi, lo, **kw))
+            arena.free(raw)
+            return Act(hi, lo, act.N, P, Q, C), P, Q
+        if train:
+            launches.append(ops.build_conv_fwd(act.hi, act.lo, w_hi, w_lo, None, M, C, spec.K, stats_only=True,
+                                               **common, **self._bn_args(spec, work, train)))
+        hi, lo = self._planes(arena, M, C)
+        kw = {}
+        if res_planes is not None:
+            kw["res_planes"] = res_planes
+        elif res_side is not None:
+            kw["res_raw"], kw["res_coef"] = res_side
+        launches.append(ops.build_conv_fwd(act.hi, act.lo, w_hi, w_lo, None, M, C, spec.K, relu=relu,
+                                           out_planes=(hi, lo), ep_coef=self._coef(spec, work), **common, **kw))
+        return Act(hi, lo, act.N, P, Q, C), P, Q
 
     def _planes(self, arena, M, C):
         hi = arena.alloc((M, C), torch.float16)
@@ -228,8 +286,7 @@ class EncoderRunner:
         return hi, lo
 
     def _side(self, raw, spec, work):
-        o, C = spec.stats_off, spec.Cout
-        return ops.bn_side(raw, work[o + 2 * C:o + 3 * C].view(torch.float32))
+        return ops.bn_side(raw, self._coef(spec, work))
 
     def _build_plan(self, N, H, W, train, dev):
         plan = _Plan()
@@ -241,8 +298,7 @@ class EncoderRunner:
         if not train:
             # eval-mode BatchNorm: coefficients from the running statistics, one tiny launch per BN layer
             for spec in self.bank.specs:
-                o, C = spec.stats_off, spec.Cout
-                launches.append(ops.build_bn_eval_coef(spec.bn, work[o + 2 * C:o + 3 * C].view(torch.float32)))
+                launches.append(ops.build_bn_eval_coef(spec.bn, self._coef(spec, work)))
         plan.idx_gather = torch.zeros((N,), device=dev, dtype=torch.int64)
         plan.idx_scatter = torch.zeros((N,), device=dev, dtype=torch.int64)
         # ---- stem (stem_pack itself is bound per call: it reads the caller's tensor) ----
@@ -268,33 +324,45 @@ class EncoderRunner:
             cur = act
             convs = blk["convs"]
             for spec in convs[:-1]:
-                raw, p_, q_ = self._build_conv(arena, cur, spec, work, train, launches)
-                hi, lo = self._planes(arena, raw.shape[0], spec.Cout)
-                launches.append(ops.build_bn_apply(self._side(raw, spec, stats), raw.shape[0], spec.Cout, True, hi, lo))
-                arena.free(raw)
+                nxt, p_, q_ = self._build_conv_planes(arena, cur, spec, work, train, launches, relu=True)
                 if cur is not act:
                     arena.free(cur.hi, cur.lo)
-                cur = Act(hi, lo, cur.N, p_, q_, spec.Cout)
+                cur = nxt
             spec = convs[-1]
-            raw, p_, q_ = self._build_conv(arena, cur, spec, work, train, launches)
+            down = blk["down"]
+            if last:
+                # last block: raw outputs feed the fused relu(bn+residual) -> NCHW + global-average-pool kernel
+                raw, p_, q_ = self._build_conv(arena, cur, spec, work, train, launches)
+                if cur is not act:
+                    arena.free(cur.hi, cur.lo)
+                kw = {}
+                raw_ds = None
+                if down is not None:
+                    raw_ds, _, _ = self._build_conv(arena, act, down, work, train, launches)
+                    kw["res_bn"] = self._side(raw_ds, down, stats)
+                else:
+                    kw["res_planes"] = (act.hi, act.lo)
+                plan.final = dict(main=self._side(raw, spec, stats), N=N, HW=p_ * q_, C=spec.Cout, kw=kw,
+                                  keep=(raw, raw_ds, act))
+                plan.out_shape = (N, spec.Cout, p_, q_)
+                break
+            raw_ds = ident = None
+            if down is None:
+                res = dict(res_planes=(act.hi, act.lo))
+            elif not train and self.fold_eval:
+                # eval: the downsample branch's BatchNorm is folded into its own epilogue -> identity planes
+                ident, _, _ = self._build_conv_planes(arena, act, down, work, train, launches, relu=False)
+                res = dict(res_planes=(ident.hi, ident.lo))
+            else:
+                raw_ds, _, _ = self._build_conv(arena, act, down, work, train, launches)
+                res = dict(res_side=(raw_ds, self._coef(down, work)))
+            nxt, p_, q_ = self._build_conv_planes(arena, cur, spec, work, train, launches, relu=True, **res)
             if cur is not act:
                 arena.free(cur.hi, cur.lo)
-            kw = {}
-            raw_ds = None
-            if blk["down"] is not None:
-                raw_ds, _, _ = self._build_conv(arena, act, blk["down"], work, train, launches)
-                kw["res_bn"] = self._side(raw_ds, blk["down"], stats)
-            else:
-                kw["res_planes"] = (act.hi, act.lo)
-            main = self._side(raw, spec, stats)
-            if last:
-                plan.final = dict(main=main, N=N, HW=p_ * q_, C=spec.Cout, kw=kw, keep=(raw, raw_ds, act))
-                plan.out_shape = (N, spec.Cout, p_, q_)
-            else:
-                hi, lo = self._planes(arena, raw.shape[0], spec.Cout)
-                launches.append(ops.build_bn_apply(main, raw.shape[0], spec.Cout, True, hi, lo, **kw))
-                arena.free(raw, raw_ds, act.hi, act.lo)
-                act = Act(hi, lo, N, p_, q_, spec.Cout)
+            arena.free(raw_ds, act.hi, act.lo)
+            if ident is not None:
+                arena.free(ident.hi, ident.lo)
+            act = nxt
         plan.launches = launches
         plan.arena_bytes = arena.total
         plan.n_static = len(launches)
@@ -330,7 +398,7 @@ class EncoderRunner:
                 raise ValueError("the jigsaw patch path keeps frames in place (no gather / scatter index)")
         with torch.cuda.device(dev):
             self.bank.refresh()
-            key = (N, H, W, bool(train), dev.index, self.bank.generation)
+            key = (N, H, W, bool(train), self.two_pass, self.fold_eval, dev.index, self.bank.generation)
             if self._plans and next(iter(self._plans))[-1] != self.bank.generation:
                 self._plans.clear()                         # parameters moved: every cached pointer is stale
             plan = self._plans.get(key)

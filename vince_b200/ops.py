@@ -70,17 +70,23 @@ def build_bn_eval_coef(bn, coef):
 
 # ---------------------------------------------------------------------------------------------------------------
 def build_conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, block_n=0, scale=None, bias=None,
-                   relu=False, stats=None, bn=None, coef=None, counter=None, halo_mode=-1, alpha=1.0):
+                   relu=False, stats=None, bn=None, coef=None, counter=None, halo_mode=-1, alpha=1.0,
+                   out_planes=None, ep_coef=None, res_planes=None, res_raw=None, res_coef=None, stats_only=False):
     """geom=None: A is [M,K]; else dict(batch,H,W,Cin,R,S,stride,pad_lo_h,pad_lo_w,pad_hi_h,pad_hi_w) (NHWC gather).
-    bn/coef/counter (with stats): fuse the train-mode BatchNorm finalize of module `bn` into the kernel tail."""
+    bn/coef/counter (with stats): fuse the train-mode BatchNorm finalize of module `bn` into the kernel tail.
+    stats_only: statistics pass (nothing stored; `out` may be None).
+    out_planes=(hi, lo) with ep_coef [2N]: "apply" epilogue - planes = relu?(acc*scale + shift + residual), residual =
+    res_planes (hi, lo) or bn(res_raw) with res_coef; `out` must be None."""
     d = _lib.ConvDesc()
     d.a_hi = _val(a_hi, torch.float16, "a_hi")
     d.a_lo = _val(a_lo, torch.float16, "a_lo")
     d.w_hi = _val(w_hi, torch.float16, "w_hi")
     d.w_lo = _val(w_lo, torch.float16, "w_lo")
     d.out = _val(out, torch.float32, "out")
-    if out.numel() < M * N:
+    if out is not None and out.numel() < M * N:
         raise ValueError("conv_fwd: output buffer too small")
+    if out is None and out_planes is None and not stats_only:
+        raise ValueError("conv_fwd: no output")
     d.M, d.N, d.K = M, N, K
     if geom is not None:
         d.im2col = 1
@@ -96,6 +102,26 @@ def build_conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, bl
     d.stats = _val(stats, torch.float64, "stats")
     d.halo_mode = halo_mode
     d.alpha = float(alpha)
+    d.stats_only = 1 if stats_only else 0
+    if out_planes is not None:
+        if out is not None or ep_coef is None:
+            raise ValueError("conv_fwd: the apply epilogue writes planes only and needs ep_coef")
+        hi, lo = out_planes
+        if hi.numel() < M * N:
+            raise ValueError("conv_fwd: output planes too small")
+        d.out_hi = _val(hi, torch.float16, "out_hi")
+        d.out_lo = _val(lo, torch.float16, "out_lo")
+        d.ep_coef = _val(ep_coef, torch.float32, "ep_coef")
+        if ep_coef.numel() < 2 * N:
+            raise ValueError("conv_fwd: ep_coef must hold [2][N] floats")
+        if res_planes is not None:
+            d.res_kind = 1
+            d.res_hi = _val(res_planes[0], torch.float16, "res_hi")
+            d.res_lo = _val(res_planes[1], torch.float16, "res_lo")
+        elif res_raw is not None:
+            d.res_kind = 2
+            d.res_raw = _val(res_raw, torch.float32, "res_raw")
+            d.res_coef = _val(res_coef, torch.float32, "res_coef")
     if bn is not None:
         if stats is None or coef is None or counter is None:
             raise ValueError("conv_fwd: the fused BatchNorm finalize needs stats, coef and counter buffers")
@@ -109,7 +135,8 @@ def build_conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, bl
         d.bn_momentum, d.bn_eps = BN_MOMENTUM, BN_EPS
     fn = _lib.lib().vince_conv_fwd
     ref = ctypes.byref(d)
-    flops = 2.0 * M * N * (geom.get("K_true", K) if geom is not None else K)
+    # algorithmic FLOPs: the statistics pass of the two-pass scheme is recomputation - it gets no credit
+    flops = 0.0 if stats_only else 2.0 * M * N * (geom.get("K_true", K) if geom is not None else K)
     check = _lib.check
 
     def run():
@@ -123,7 +150,8 @@ def build_conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, bl
             PROFILE.append(("conv_gemm", flops, e0, e1))
         else:
             check(fn(ref, stream), "vince_conv_fwd")
-    run._keep = (d, a_hi, a_lo, w_hi, w_lo, out, scale, bias, stats, bn, coef, counter)
+    run._keep = (d, a_hi, a_lo, w_hi, w_lo, out, scale, bias, stats, bn, coef, counter, out_planes, ep_coef, res_planes,
+                 res_raw, res_coef)
     return run
 
 
