@@ -31,6 +31,10 @@ SHAPES = [
     ("r50.layer2 1x1 512->128", 28, 28, 512, 128, 1, 1, 0),
     ("r50.layer3 1x1 1024->256", 14, 14, 1024, 256, 1, 1, 0),
     ("r50.layer4 1x1 512->2048", 7, 7, 512, 2048, 1, 1, 0),
+    ("r50.layer3 1x1 256->1024", 14, 14, 256, 1024, 1, 1, 0),
+    ("r50.layer2 1x1 256->128", 56, 56, 256, 128, 1, 1, 0),
+    ("r50.layer4 1x1 2048->512", 7, 7, 2048, 512, 1, 1, 0),
+    ("r50.layer3 3x3", 14, 14, 256, 256, 3, 1, 1),
 ]
 
 
@@ -43,6 +47,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--passes", type=int, default=3)
     ap.add_argument("--nostats", action="store_true")
+    ap.add_argument("--statsonly", action="store_true")
     a = ap.parse_args()
     dev = "cuda"
     B = a.batch
@@ -69,8 +74,9 @@ def main():
             x_hi = hi.reshape(-1, Cin) if geom is None else hi
             x_lo = lo.reshape(-1, Cin) if geom is None else lo
             runs.append(ops.build_conv_fwd(x_hi, x_lo if a.passes == 3 else None, w_hi, w_lo if a.passes == 3 else None,
-                                           outs[i], M, Cout, K, passes=a.passes, geom=geom, block_n=a.bn,
-                                           stats=None if a.nostats else stats, halo_mode=a.halo))
+                                           None if a.statsonly else outs[i], M, Cout, K, passes=a.passes, geom=geom,
+                                           block_n=a.bn, stats=None if a.nostats else stats, halo_mode=a.halo,
+                                           stats_only=a.statsonly))
         for r in runs:
             r()
         torch.cuda.synchronize()

@@ -460,6 +460,7 @@ def test_fused_epilogue_routes_equal_separate_bn_apply_bitwise(backbone, B, H):
     x = torch.randn((B, 3, H, H), generator=gen).to(DEV)
     snap = {k: v.clone() for k, v in model.state_dict().items()}
     res = {}
+    import time
     for mode, train in (("separate", True), ("fused", True), ("separate", False), ("fused", False)):
         model.load_state_dict(snap)
         model.train(train)

@@ -96,6 +96,22 @@ __device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 
+// ---- cp.async (LDGSTS): 16-byte asynchronous global -> shared copies, no register staging ----
+__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Error-free accumulation (Knuth TwoSum): (s, e) += x with s + e carrying the exact running sum to ~2^-48 relative.
+__device__ __forceinline__ void two_sum_acc(float& s, float& e, float x) {
+  const float t = __fadd_rn(s, x);
+  const float bp = __fadd_rn(t, -s);
+  const float err = __fadd_rn(__fadd_rn(s, -__fadd_rn(t, -bp)), __fadd_rn(x, -bp));
+  e = __fadd_rn(e, err);
+  s = t;
+}
+
 // ---- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

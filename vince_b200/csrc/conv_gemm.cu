@@ -41,6 +41,8 @@ constexpr size_t SMEM_BUDGET = 226 * 1024;    // of 227 KB: leaves the 1 KB syst
 struct GemmKernelParams {
   CUtensorMap a_hi, a_lo, b_hi, b_lo, out;
   CUtensorMap out_hi, out_lo;    // EPI == 1: fp16 (hi, lo) output planes (box 32 channels x 128 rows, SWIZZLE_64B)
+  int staging_bufs;              // output staging tiles in shared memory (1 or 2)
+  uint32_t staging_total;        // bytes of the staging area: staging_bufs output tiles (+ 2 residual tiles, EPI == 1)
   // EPI == 1 ("apply" epilogue): out = relu?( acc*alpha*coef[c] + coef[N+c] + residual ) split into fp16 planes
   const float* ep_coef;          // [2][N] per-channel (scale, shift): BatchNorm coefficients
   int res_kind;                  // 0 none, 1 fp16 planes [M,N], 2 bn(res_raw) with res_coef (downsample branch)
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
   uint8_t* a_ring = smem;
   uint8_t* b_ring = a_ring + (size_t)p.a_stages * a_stage_bytes;
   uint8_t* staging = b_ring + (size_t)p.b_stages * b_stage_bytes;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(staging + p.staging_total);
   uint64_t* a_empty = a_full + MAX_RING;
   uint64_t* b_full = a_empty + MAX_RING;
   uint64_t* b_empty = b_full + MAX_RING;
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
     }
   }
   if (threadIdx.x >= EPI_TID0) {
-    for (int i = threadIdx.x - EPI_TID0; i < 8 * BN; i += 128) smem_stats[i] = 0.0;
+    for (int i = threadIdx.x - EPI_TID0; i < 8 * BN + 2; i += 128) smem_stats[i] = 0.0;
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -442,12 +444,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
       }
     }
   } else {
-    // ======================= epilogue (warps 2..5) =======================
+    // ======================= epilogue (warps 5..8) =======================
+    // Per 32-column chunk: TMEM -> registers (one accumulator row per thread) -> epilogue math -> swizzled staging
+    // tile in shared memory -> one named barrier -> TMA store (asynchronous: the copy-out costs the SM's LSU nothing;
+    // coalesced st.global from the staged tile was measured 1.6x SLOWER on the wide layers) plus, for train-mode
+    // BatchNorm, column sums read back from the staged tile.  With two staging tiles (small-K, epilogue-bound layers)
+    // the store of chunk j drains while chunk j+1 is produced and a chunk costs ONE barrier; with one tile the
+    // round-1 scheme (wait for the store, barrier, write, barrier) is kept.
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const int etid = threadIdx.x - EPI_TID0;       // 0..127
-    const bool store_leader = (etid == 0);
     const uint32_t staging_s = smem_u32(staging);
+    const int nbuf = p.staging_bufs;               // 1 or 2 output staging tiles
+    // kernel parameters used per chunk, read once (the asm barriers would otherwise force constant-bank re-reads)
+    const bool has_stats = (EPI == 0) && p.stats != nullptr;
+    const bool do_store = p.stats_only == 0;
+    const float alpha = p.alpha;
+    const int N = p.N;
+    const long long M = p.M;
+    const int relu = p.relu;
+    const int res_kind = (EPI == 1) ? p.res_kind : 0;
+    const bool store_leader = (etid == 0);
+    bool store_pending = false;
+    const float* const ep_scale = p.scale;
+    const float* const ep_bias = p.bias;
+    const uint32_t stats_s = smem_u32(smem_stats + 1);        // 16-byte aligned: [4 warps][BN] x {sum, err, sq, err}
+    const uint32_t res_s = staging_s + (uint32_t)nbuf * STAGING_BYTES;      // EPI == 1: two residual tiles
     // halo mode: which output pixel (if any) this accumulator row is
     int hy = 0, hx = 0;
     if (HALO) {
@@ -456,160 +478,198 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
     }
     int local_t = 0;
     int cur_n_blk = -1;
-    bool store_pending = false;
+    uint32_t chunk_ctr = 0;
     uint32_t tmem_empty_leader[2] = {0u, 0u};
     if (CG == 2) {
       tmem_empty_leader[0] = mapa_shared(smem_u32(&tmem_empty[0]), 0);
       tmem_empty_leader[1] = mapa_shared(smem_u32(&tmem_empty[1]), 0);
     }
-    for (int tile = tile_start; tile < num_tiles; tile += tile_step, ++local_t) {
+    // first global row and number of valid staging rows of a tile
+    auto tile_rows = [&](int tile, long long& m0, int& nvalid, int& n_blk) {
       const int m_blk = (tile % p.num_m_blocks) * CG + (int)cta_rank;
-      const int n_blk = tile / p.num_m_blocks;
+      n_blk = tile / p.num_m_blocks;
+      if (HALO) {
+        const int img = m_blk / p.tiles_per_img;
+        const int y0 = (m_blk - img * p.tiles_per_img) * p.TH;
+        m0 = ((long long)img * p.H + y0) * p.W;             // TH full image rows are contiguous in NHWC
+        nvalid = min(p.TH, p.H - y0) * p.W;
+      } else {
+        m0 = (long long)m_blk * BM;
+        nvalid = BM;
+      }
+      if (m0 + nvalid > M) nvalid = (int)(M - m0 > 0 ? M - m0 : 0);
+    };
+    // EPI == 1: asynchronous, coalesced prefetch (cp.async, 16 bytes per request) of the residual tile of (tile,
+    // chunk) into residual buffer `rbuf`, laid out with the same XOR swizzles as the output staging tiles so that the
+    // row-owner reads below are bank-conflict free
+    auto prefetch_residual = [&](int tile, int chunk, uint32_t rbuf) {
+      if (res_kind != 0 && tile < num_tiles) {
+        long long m0;
+        int nvalid, n_blk;
+        tile_rows(tile, m0, nvalid, n_blk);
+        const int c0 = n_blk * BN + chunk * 32;
+        const uint32_t dst = res_s + rbuf * STAGING_BYTES;
+        if (res_kind == 1) {
+          const int piece = etid & 3, r0 = etid >> 2;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int sr = r0 + 32 * j;
+            if (sr < nvalid) {
+              const uint32_t off = (uint32_t)(sr * 64 + ((piece ^ ((sr >> 1) & 3)) << 4));
+              const long long g = (m0 + sr) * N + c0 + piece * 8;
+              cp_async_16(dst + off, p.res_hi + g);
+              if (p.res_lo != nullptr) cp_async_16(dst + 8192u + off, p.res_lo + g);
+            }
+          }
+        } else {
+          const int piece = etid & 7, r0 = etid >> 3;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int sr = r0 + 16 * j;
+            if (sr < nvalid)
+              cp_async_16(dst + (uint32_t)(sr * 128 + ((piece ^ (sr & 7)) << 4)), p.res_raw + (m0 + sr) * N + c0 + piece * 4);
+          }
+        }
+      }
+      cp_async_commit();
+    };
+    if (EPI == 1) prefetch_residual(tile_start, 0, 0u);
+    for (int tile = tile_start; tile < num_tiles; tile += tile_step, ++local_t) {
       const int acc = local_t & 1;
       const uint32_t acc_phase = (local_t >> 1) & 1;
-      int img = 0, y0 = 0;
-      bool valid = true;
-      int srow = row;                              // row inside the staging tile
-      int nvalid = BM;                             // staging rows [0, nvalid) hold this tile's outputs
+      long long m0;
+      int nvalid, n_blk;
+      tile_rows(tile, m0, nvalid, n_blk);
+      const int m_blk = (tile % p.num_m_blocks) * CG + (int)cta_rank;
+      int img = 0, y0 = 0;                         // halo mode: TMA store coordinates of the tile
       if (HALO) {
         img = m_blk / p.tiles_per_img;
         y0 = (m_blk - img * p.tiles_per_img) * p.TH;
-        valid = (hy < p.TH) && (hx < p.W) && (y0 + hy < p.H);
-        srow = hy * p.W + hx;
-        nvalid = min(p.TH, p.H - y0) * p.W;
       }
+      bool valid = true;
+      int srow = row;                              // row inside the staging tile
+      if (HALO) {
+        valid = (hy < p.TH) && (hx < p.W);
+        srow = hy * p.W + hx;
+      }
+      valid = valid && srow < nvalid;
       if (EPI == 1 && n_blk != cur_n_blk) {
         // per-channel coefficients of this n-block, cached in the (otherwise unused) statistics area:
         // [0,BN) scale  [BN,2BN) shift  [2BN,3BN) residual scale  [3BN,4BN) residual shift
-        float* cf = reinterpret_cast<float*>(smem_stats);
+        float* cf = reinterpret_cast<float*>(smem_stats + 1);      // +8 bytes: 16-byte aligned for the vector reads
         named_bar_sync(1, 128);                    // readers of the previous n-block's coefficients are done
         for (int i = etid; i < BN; i += 128) {
           const int c = n_blk * BN + i;
-          const bool ok = c < p.N;
+          const bool ok = c < N;
           cf[i] = ok ? __ldg(p.ep_coef + c) : 0.f;
-          cf[BN + i] = ok ? __ldg(p.ep_coef + p.N + c) : 0.f;
-          if (p.res_kind == 2) {
+          cf[BN + i] = ok ? __ldg(p.ep_coef + N + c) : 0.f;
+          if (res_kind == 2) {
             cf[2 * BN + i] = ok ? __ldg(p.res_coef + c) : 0.f;
-            cf[3 * BN + i] = ok ? __ldg(p.res_coef + p.N + c) : 0.f;
+            cf[3 * BN + i] = ok ? __ldg(p.res_coef + N + c) : 0.f;
           }
         }
         named_bar_sync(1, 128);
         cur_n_blk = n_blk;
       }
-      if (EPI == 0 && p.stats != nullptr && n_blk != cur_n_blk) {
+      if (has_stats && n_blk != cur_n_blk) {
         if (cur_n_blk >= 0) {
           named_bar_sync(1, 128);
           for (int i = etid; i < BN; i += 128) {
             double a = 0.0, b = 0.0;
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
-              a += smem_stats[w * 2 * BN + i];
-              b += smem_stats[w * 2 * BN + BN + i];
-              smem_stats[w * 2 * BN + i] = 0.0;
-              smem_stats[w * 2 * BN + BN + i] = 0.0;
+              const uint32_t slot = stats_s + (uint32_t)(w * BN + i) * 16u;
+              const float4 t = lds_v4(slot);
+              a += (double)t.x + (double)t.y;
+              b += (double)t.z + (double)t.w;
+              sts_v4(slot, make_float4(0.f, 0.f, 0.f, 0.f));
             }
-            if (cur_n_blk * BN + i < p.N) {
+            if (cur_n_blk * BN + i < N) {
               atomicAdd(&p.stats[cur_n_blk * BN + i], a);
-              atomicAdd(&p.stats[p.N + cur_n_blk * BN + i], b);
+              atomicAdd(&p.stats[N + cur_n_blk * BN + i], b);
             }
           }
           named_bar_sync(1, 128);
         }
         cur_n_blk = n_blk;
       }
-      // EPI == 1: global row of this accumulator row (residual address)
-      long long m_row = 0;
-      bool row_ok = valid;
-      if (EPI == 1) {
-        if (HALO) m_row = ((long long)img * p.H + (y0 + hy)) * p.W + hx;
-        else m_row = (long long)m_blk * BM + row;
-        row_ok = valid && m_row < (long long)p.M;
-      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       if (etid == 0) VB_TRACE_EVENT(3, local_t);
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      for (int chunk = 0; chunk < BN / 32; ++chunk, ++chunk_ctr) {
+        const int c0 = n_blk * BN + chunk * 32;
+        const uint32_t buf = staging_s + (nbuf == 2 ? (chunk_ctr & 1u) * STAGING_BYTES : 0u);
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk * 32, raw);
+        tmem_ld_wait();
+        if (chunk == BN / 32 - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before_sync();
+          if (CG == 2) {
+            // the leader's MMA warp owns both accumulators: one remote arrive per epilogue warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tmem_empty_leader[acc]);
+          } else {
+            mbar_arrive(&tmem_empty[acc]);
+          }
+        }
         if (EPI == 1) {
-          const int c0 = n_blk * BN + chunk * 32;
-          // residual loads first: their latency hides behind the TMEM load
-          // one register buffer for either residual kind: planes -> rb[0..3] = 32 hi halves, rb[4..7] = 32 lo halves;
-          // raw -> rb[j] = fp32 channels 4j .. 4j+3
-          uint4 rb[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) rb[j] = make_uint4(0u, 0u, 0u, 0u);
-          if (p.res_kind == 1) {
-            if (row_ok) {
-              const uint4* ph = reinterpret_cast<const uint4*>(p.res_hi + m_row * p.N + c0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) rb[j] = __ldg(ph + j);
-              if (p.res_lo != nullptr) {
-                const uint4* pl = reinterpret_cast<const uint4*>(p.res_lo + m_row * p.N + c0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) rb[4 + j] = __ldg(pl + j);
-              }
-            }
-          } else if (p.res_kind == 2) {
-            if (row_ok) {
-              const uint4* pr = reinterpret_cast<const uint4*>(p.res_raw + m_row * p.N + c0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) rb[j] = __ldg(pr + j);
-            }
+          const uint32_t rcur = res_s + (chunk_ctr & 1u) * STAGING_BYTES;
+          // residual tile of THIS chunk has landed (mine: wait_group; everybody's: the barrier), and every thread is
+          // done with the output staging tile / the residual tile of two chunks ago
+          if (res_kind != 0) cp_async_wait_all();
+          if (nbuf == 1 && store_leader && store_pending) tma_store_wait_read0();
+          if (res_kind != 0 || nbuf == 1) named_bar_sync(2, 128);
+          {
+            // prefetch the next chunk's residual tile into the other buffer
+            int nt = tile, nc = chunk + 1;
+            if (nc == BN / 32) nt = tile + tile_step, nc = 0;
+            prefetch_residual(nt, nc, (chunk_ctr + 1u) & 1u);
           }
-          uint32_t raw[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk * 32, raw);
-          tmem_ld_wait();
-          if (chunk == BN / 32 - 1) {
-            tc_fence_before_sync();
-            if (CG == 2) {
-              __syncwarp();
-              if (lane == 0) mbar_arrive_cluster(tmem_empty_leader[acc]);
-            } else {
-              mbar_arrive(&tmem_empty[acc]);
-            }
-          }
-          const uint32_t cfs = smem_u32(smem_stats) + (uint32_t)(chunk * 32) * 4u;
-          // the staging tile must have been drained by the previous chunk's TMA store before anybody writes it
-          if (store_leader && store_pending) tma_store_wait_read0();
-          named_bar_sync(2, 128);
-          // two 8 KB tiles (hi | lo) of 64-byte rows; 16-byte chunk j of row `srow` stored at j ^ ((srow >> 1) & 3):
-          // SWIZZLE_64B (address bits [4,5] ^= bits [7,8]), conflict-free.  One 8-channel group at a time keeps the
-          // live registers at raw[32] + residual[32] + a handful.
-          const uint32_t rowp = staging_s + (uint32_t)srow * 64u;
+          const uint32_t cfs = stats_s + (uint32_t)(chunk * 32) * 4u;
+          // two 8 KB tiles (hi | lo) of 64-byte rows; 16-byte piece j of row `srow` stored at j ^ ((srow >> 1) & 3),
+          // conflict-free.  One 8-channel group at a time keeps the live registers at raw[32] + a handful.
           const uint32_t sw = (uint32_t)((srow >> 1) & 3);
+          const uint32_t rowp = buf + (uint32_t)srow * 64u;
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
             float v[8];
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               const float4 sc = lds_v4(cfs + (2 * g8 + q) * 16), sh = lds_v4(cfs + BN * 4 + (2 * g8 + q) * 16);
-              v[4 * q + 0] = fmaf(__uint_as_float(raw[8 * g8 + 4 * q + 0]) * p.alpha, sc.x, sh.x);
-              v[4 * q + 1] = fmaf(__uint_as_float(raw[8 * g8 + 4 * q + 1]) * p.alpha, sc.y, sh.y);
-              v[4 * q + 2] = fmaf(__uint_as_float(raw[8 * g8 + 4 * q + 2]) * p.alpha, sc.z, sh.z);
-              v[4 * q + 3] = fmaf(__uint_as_float(raw[8 * g8 + 4 * q + 3]) * p.alpha, sc.w, sh.w);
+              v[4 * q + 0] = fmaf(__uint_as_float(raw[8 * g8 + 4 * q + 0]) * alpha, sc.x, sh.x);
+              v[4 * q + 1] = fmaf(__uint_as_float(raw[8 * g8 + 4 * q + 1]) * alpha, sc.y, sh.y);
+              v[4 * q + 2] = fmaf(__uint_as_float(raw[8 * g8 + 4 * q + 2]) * alpha, sc.z, sh.z);
+              v[4 * q + 3] = fmaf(__uint_as_float(raw[8 * g8 + 4 * q + 3]) * alpha, sc.w, sh.w);
             }
-            if (p.res_kind == 1) {
-              const uint32_t hw[4] = {rb[g8].x, rb[g8].y, rb[g8].z, rb[g8].w};
-              const uint32_t lw[4] = {rb[4 + g8].x, rb[4 + g8].y, rb[4 + g8].z, rb[4 + g8].w};
+            if (res_kind == 1) {
+              const uint32_t off = (uint32_t)(srow * 64 + ((g8 ^ sw) << 4));
+              const float4 fh = valid ? lds_v4(rcur + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 fl = (valid && p.res_lo != nullptr) ? lds_v4(rcur + 8192u + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const uint32_t hw[4] = {__float_as_uint(fh.x), __float_as_uint(fh.y), __float_as_uint(fh.z), __float_as_uint(fh.w)};
+              const uint32_t lw[4] = {__float_as_uint(fl.x), __float_as_uint(fl.y), __float_as_uint(fl.z), __float_as_uint(fl.w)};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const __half2 a = *reinterpret_cast<const __half2*>(&hw[i]), b = *reinterpret_cast<const __half2*>(&lw[i]);
-                v[2 * i] += __low2float(a) + __low2float(b);
-                v[2 * i + 1] += __high2float(a) + __high2float(b);
+                const __half2 ha = *reinterpret_cast<const __half2*>(&hw[i]), hb = *reinterpret_cast<const __half2*>(&lw[i]);
+                v[2 * i] += __low2float(ha) + __low2float(hb);
+                v[2 * i + 1] += __high2float(ha) + __high2float(hb);
               }
-            } else if (p.res_kind == 2) {
+            } else if (res_kind == 2) {
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
                 const float4 rsc = lds_v4(cfs + 2 * BN * 4 + (2 * g8 + q) * 16);
                 const float4 rsh = lds_v4(cfs + 3 * BN * 4 + (2 * g8 + q) * 16);
-                const uint4 r4 = rb[2 * g8 + q];
-                v[4 * q + 0] += fmaf(__uint_as_float(r4.x), rsc.x, rsh.x);
-                v[4 * q + 1] += fmaf(__uint_as_float(r4.y), rsc.y, rsh.y);
-                v[4 * q + 2] += fmaf(__uint_as_float(r4.z), rsc.z, rsh.z);
-                v[4 * q + 3] += fmaf(__uint_as_float(r4.w), rsc.w, rsh.w);
+                const int pj = 2 * g8 + q;
+                const float4 r4 = valid ? lds_v4(rcur + (uint32_t)(srow * 128 + ((pj ^ (srow & 7)) << 4)))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[4 * q + 0] += fmaf(r4.x, rsc.x, rsh.x);
+                v[4 * q + 1] += fmaf(r4.y, rsc.y, rsh.y);
+                v[4 * q + 2] += fmaf(r4.z, rsc.z, rsh.z);
+                v[4 * q + 3] += fmaf(r4.w, rsc.w, rsh.w);
               }
             }
-            if (p.relu) {
+            if (relu) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
             }
@@ -632,79 +692,74 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
             }
           }
           fence_proxy_async_smem();
-          named_bar_sync(2, 128);
+          // two tiles: the PREVIOUS chunk's store (other tile) must have drained before the barrier lets anybody start
+          // the next chunk, which overwrites that tile
+          if (nbuf == 2 && store_leader && store_pending) tma_store_wait_read0();
+          named_bar_sync(3, 128);
           if (store_leader) {
+            const void* src = staging + (buf - staging_s);
             if (HALO) {
-              tma_store_4d(&p.out_hi, staging, c0, 0, y0, img);
-              if (planes == 2) tma_store_4d(&p.out_lo, staging + 8192, c0, 0, y0, img);
+              tma_store_4d(&p.out_hi, src, c0, 0, y0, img);
+              if (planes == 2) tma_store_4d(&p.out_lo, reinterpret_cast<const uint8_t*>(src) + 8192, c0, 0, y0, img);
             } else {
-              tma_store_2d(&p.out_hi, staging, c0, m_blk * BM);
-              if (planes == 2) tma_store_2d(&p.out_lo, staging + 8192, c0, m_blk * BM);
+              tma_store_2d(&p.out_hi, src, c0, m_blk * BM);
+              if (planes == 2) tma_store_2d(&p.out_lo, reinterpret_cast<const uint8_t*>(src) + 8192, c0, m_blk * BM);
             }
             tma_store_commit();
           }
           store_pending = true;
           continue;
         }
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk * 32, raw);
-        tmem_ld_wait();
-        if (chunk == BN / 32 - 1) {
-          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-          tc_fence_before_sync();
-          if (CG == 2) {
-            // the leader's MMA warp owns both accumulators: one remote arrive per epilogue warp
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(tmem_empty_leader[acc]);
-          } else {
-            mbar_arrive(&tmem_empty[acc]);
-          }
-        }
         float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = valid ? __uint_as_float(raw[i]) * p.alpha : 0.f;
-        const int c0 = n_blk * BN + chunk * 32;
-        if (p.scale != nullptr) {
+        for (int i = 0; i < 32; ++i) v[i] = valid ? __uint_as_float(raw[i]) * alpha : 0.f;
+        if (ep_scale != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= (c0 + i < p.N) ? __ldg(p.scale + c0 + i) : 0.f;
+          for (int i = 0; i < 32; ++i) v[i] *= (c0 + i < N) ? __ldg(ep_scale + c0 + i) : 0.f;
         }
-        if (p.bias != nullptr) {
+        if (ep_bias != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += (c0 + i < p.N) ? __ldg(p.bias + c0 + i) : 0.f;
+          for (int i = 0; i < 32; ++i) v[i] += (c0 + i < N) ? __ldg(ep_bias + c0 + i) : 0.f;
         }
-        if (p.relu) {
+        if (relu) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        // staging buffer must have been drained by the previous TMA store
-        if (store_leader && store_pending) tma_store_wait_read0();
-        named_bar_sync(2, 128);
+        // one staging tile: everybody must be done reading the previous chunk before it is overwritten; two tiles:
+        // the barrier below (of the previous chunk) already guarantees that for the tile of two chunks ago
+        if (nbuf == 1) {
+          if (store_leader && store_pending) tma_store_wait_read0();
+          named_bar_sync(2, 128);
+        }
         if (valid) {
-          // 128-byte row `srow`, 16-byte chunk j stored at (j ^ (srow & 7)) : SWIZZLE_128B, conflict-free
-          const uint32_t rowp = staging_s + (uint32_t)srow * 128u;
+          // 128-byte row `srow`, 16-byte piece j stored at (j ^ (srow & 7)): SWIZZLE_128B, conflict-free
+          const uint32_t rowp = buf + (uint32_t)srow * 128u;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             sts_v4(rowp + (uint32_t)((j ^ (srow & 7)) << 4), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
         }
-        fence_proxy_async_smem();
-        named_bar_sync(2, 128);
-        if (!p.stats_only) {
+        if (do_store) {
+          fence_proxy_async_smem();
+          if (nbuf == 2 && store_leader && store_pending) tma_store_wait_read0();
+        }
+        named_bar_sync(3, 128);
+        if (do_store) {
           if (store_leader) {
-            if (HALO) tma_store_4d(&p.out, staging, c0, 0, y0, img);
-            else tma_store_2d(&p.out, staging, c0, m_blk * BM);
+            const void* src = staging + (buf - staging_s);
+            if (HALO) tma_store_4d(&p.out, src, c0, 0, y0, img);
+            else tma_store_2d(&p.out, src, c0, m_blk * BM);
             tma_store_commit();
           }
           store_pending = true;
         }
-        if (p.stats != nullptr) {
-          // BatchNorm sums from the staged tile (the raw accumulators the TMA store is reading): warp w adds up its
-          // 32 staging rows of column `lane` (conflict-free 128-byte row reads, four independent chains) into the
-          // warp-private fp64 accumulators - ~130 instructions per chunk where a register transpose-reduce (butterfly
-          // of 62 shuffles + 124 selects) needs ~370; measured 8-18 % faster on the epilogue-bound layers (stem, N=64,
-          // small-K 1x1).  The next chunk's first barrier keeps the tile alive until every warp is done.
+        if (has_stats) {
+          // BatchNorm sums from the staged tile: warp w adds up its 32 staging rows of column `lane` (conflict-free
+          // 128-byte row reads, four independent chains) and folds the two partial sums into warp-private
+          // double-float (sum, error) accumulators with an error-free TwoSum - fp64-grade accumulation at the cost of
+          // a dozen FADDs (fp64 adds cost 25 % of the epilogue's stall samples on this part, profiles/r02_summary.md)
           const int r_end = min(32, nvalid - quarter * 32);
           float sa = 0.f, sb = 0.f, sc = 0.f, sd = 0.f, qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f;
-          const uint32_t base = staging_s + (uint32_t)((quarter * 32) * 128 + ((lane & 3) << 2));
+          const uint32_t base = buf + (uint32_t)((quarter * 32) * 128 + ((lane & 3) << 2));
           const int cj = lane >> 2;
           if (r_end == 32) {
 #pragma unroll
@@ -723,22 +778,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
               qa = fmaf(x0, x0, qa);
             }
           }
-          const uint32_t my = smem_u32(smem_stats) + (uint32_t)(quarter * 2 * BN + chunk * 32 + lane) * 8u;
-          sts_f64(my, lds_f64(my) + (double)((sa + sb) + (sc + sd)));
-          sts_f64(my + BN * 8u, lds_f64(my + BN * 8u) + (double)((qa + qb) + (qc + qd)));
+          const uint32_t my = stats_s + (uint32_t)(quarter * BN + chunk * 32 + lane) * 16u;
+          float4 t = lds_v4(my);
+          two_sum_acc(t.x, t.y, (sa + sb) + (sc + sd));
+          two_sum_acc(t.z, t.w, (qa + qb) + (qc + qd));
+          sts_v4(my, t);
         }
       }
     }
-    if (EPI == 0 && p.stats != nullptr) {
+    if (EPI == 1) cp_async_wait_all();
+    if (store_leader) tma_store_wait0();
+    if (has_stats) {
       if (cur_n_blk >= 0) {
         named_bar_sync(1, 128);
         for (int i = etid; i < BN; i += 128) {
           double a = 0.0, b = 0.0;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) a += smem_stats[w * 2 * BN + i], b += smem_stats[w * 2 * BN + BN + i];
-          if (cur_n_blk * BN + i < p.N) {
+          for (int w = 0; w < 4; ++w) {
+            const float4 t = lds_v4(stats_s + (uint32_t)(w * BN + i) * 16u);
+            a += (double)t.x + (double)t.y;
+            b += (double)t.z + (double)t.w;
+          }
+          if (cur_n_blk * BN + i < N) {
             atomicAdd(&p.stats[cur_n_blk * BN + i], a);
-            atomicAdd(&p.stats[p.N + cur_n_blk * BN + i], b);
+            atomicAdd(&p.stats[N + cur_n_blk * BN + i], b);
           }
         }
       }
@@ -754,9 +817,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
         named_bar_sync(1, 128);
         if (*last_flag) {
           __threadfence();
-          for (int c = etid; c < p.N; c += 128) {
+          for (int c = etid; c < N; c += 128) {
             const double mean = __ldcg(&p.stats[c]) / p.bn_count;
-            double var = __ldcg(&p.stats[p.N + c]) / p.bn_count - mean * mean;
+            double var = __ldcg(&p.stats[N + c]) / p.bn_count - mean * mean;
             if (var < 0.0) var = 0.0;
             const double unbiased = p.bn_count > 1.0 ? var * (p.bn_count / (p.bn_count - 1.0)) : var;
             p.bn_running_mean[c] =
@@ -766,13 +829,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
             const float inv = (float)(1.0 / sqrt(var + (double)p.bn_eps));
             const float sc = p.bn_gamma[c] * inv;
             p.bn_coef[c] = sc;
-            p.bn_coef[p.N + c] = p.bn_beta[c] - (float)mean * sc;
+            p.bn_coef[N + c] = p.bn_beta[c] - (float)mean * sc;
           }
           if (etid == 0 && p.bn_nbt != nullptr) *p.bn_nbt += 1;
         }
       }
     }
-    if (store_leader) tma_store_wait0();
   }
 
   tc_fence_before_sync();
@@ -825,8 +887,20 @@ static int num_sms() {
   return sms[dev];
 }
 
-static size_t fixed_smem(int bn) {
-  return 1024 /*align slack*/ + STAGING_BYTES + (4 * MAX_RING + 4) * 8 + 16 + 8 * bn * 8;
+// Output staging tiles: two (one barrier per chunk instead of two) when a tile has few k-blocks, i.e. when the layer is
+// bound by its epilogue and shared memory is not needed for a deep operand ring; plus two residual tiles for the apply
+// epilogue with a residual.
+static int staging_tiles(const ConvGemmDesc& d) {
+  int nbuf = (d.K / BK <= 8) ? 2 : 1;
+  const char* e = getenv("VINCE_B200_STAGING");      // debug / A-B comparison: 1 or 2
+  if (e && (atoi(e) == 1 || atoi(e) == 2)) nbuf = atoi(e);
+  return nbuf;
+}
+static size_t staging_bytes(const ConvGemmDesc& d) {
+  return (size_t)STAGING_BYTES * (staging_tiles(d) + ((d.out_hi != nullptr && d.res_kind != 0) ? 2 : 0));
+}
+static size_t fixed_smem(int bn, const ConvGemmDesc& d) {
+  return 1024 /*align slack*/ + staging_bytes(d) + (4 * MAX_RING + 4) * 8 + 32 + 8 * bn * 8;
 }
 
 template <int BN, int CG, bool HALO, bool RES, int EPI>
@@ -875,7 +949,7 @@ static int auto_block_n(const ConvGemmDesc& d, int cg) {
       // a 2-stage ring of (A tile + this CTA's weight share) must fit next to the fixed buffers
       const size_t planes = d.passes == 3 ? 2 : 1;
       const size_t stage = ((size_t)BM * 128 + (size_t)(bn / cg) * 128) * planes;
-      if (bn > 64 && fixed_smem(bn) + 2 * stage > SMEM_BUDGET) continue;
+      if (bn > 64 && fixed_smem(bn, d) + 2 * stage > SMEM_BUDGET) continue;
     }
     const long tiles = m_blocks * ((d.N + bn - 1) / bn);
     const long waves = (tiles + units - 1) / units;
@@ -914,7 +988,7 @@ static int halo_tile_rows(const ConvGemmDesc& d) {
   const size_t planes = d.passes == 3 ? 2 : 1;
   const size_t a_stage = (size_t)(((th + 2) * Wp + 7) / 8) * 1024 * planes;
   const size_t b_stage = (size_t)bn * 128 * planes;
-  if (fixed_smem(bn) + 2 * a_stage + 2 * b_stage > SMEM_BUDGET) return 0;
+  if (fixed_smem(bn, d) + 2 * a_stage + 2 * b_stage > SMEM_BUDGET) return 0;
   return th;
 }
 
@@ -1010,20 +1084,6 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
                               th + 2, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }
-    if (planes_out) {
-      rc = encode_tma_4d_nhwc(&kp.out_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.out_hi, d.batch, d.H, d.W, d.N, 32, d.W, th,
-                              CU_TENSOR_MAP_SWIZZLE_64B);
-      if (rc) return rc;
-      if (d.out_lo) {
-        rc = encode_tma_4d_nhwc(&kp.out_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.out_lo, d.batch, d.H, d.W, d.N, 32, d.W,
-                                th, CU_TENSOR_MAP_SWIZZLE_64B);
-        if (rc) return rc;
-      }
-    } else if (d.out) {
-      rc = encode_tma_4d_nhwc(&kp.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.out, d.batch, d.H, d.W, d.N, 32, d.W, th,
-                              CU_TENSOR_MAP_SWIZZLE_128B);
-      if (rc) return rc;
-    }
   } else if (d.im2col) {
     const int P = (d.H + d.pad_lo_h + d.pad_hi_h - d.R) / d.stride + 1;
     const int Q = (d.W + d.pad_lo_w + d.pad_hi_w - d.S) / d.stride + 1;
@@ -1064,7 +1124,23 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
                        CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  if (kp.a_mode != 2) {
+  if (kp.a_mode == 2) {
+    const int th_ = kp.TH;
+    if (planes_out) {
+      rc = encode_tma_4d_nhwc(&kp.out_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.out_hi, d.batch, d.H, d.W, d.N, 32, d.W, th_,
+                              CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+      if (d.out_lo) {
+        rc = encode_tma_4d_nhwc(&kp.out_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.out_lo, d.batch, d.H, d.W, d.N, 32, d.W,
+                                th_, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+      }
+    } else if (d.out) {
+      rc = encode_tma_4d_nhwc(&kp.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.out, d.batch, d.H, d.W, d.N, 32, d.W, th_,
+                              CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+  } else {
     if (planes_out) {
       rc = encode_tma_2d(&kp.out_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.out_hi, d.N, d.M, (uint64_t)d.N * 2, 32, BM,
                          CU_TENSOR_MAP_SWIZZLE_64B);
@@ -1080,11 +1156,13 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
       if (rc) return rc;
     }
   }
+  kp.staging_bufs = staging_tiles(d);
+  kp.staging_total = (uint32_t)staging_bytes(d);
 
   // ---- shared-memory budget: A ring + B ring ----
   const size_t a_stage = (size_t)kp.a_plane_bytes * planes;
   const size_t b_stage = (size_t)(bn / cg) * 128 * planes;
-  const size_t avail = SMEM_BUDGET - fixed_smem(bn);
+  const size_t avail = SMEM_BUDGET - fixed_smem(bn, d);
   // resident weights: single n-block, this CTA's whole weight share + two activation stages fit, and every CTA
   // works through several tiles (otherwise the ring version overlaps the weight load just as well)
   const int total_kb = kp.a_chunks * kp.b_per_a;
@@ -1110,7 +1188,7 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
     VB_REQUIRE(st >= 2, "conv_gemm: not enough shared memory for a 2-stage pipeline (bn=%d)", bn);
     kp.a_stages = kp.b_stages = st;
   }
-  const size_t smem = fixed_smem(bn) + kp.a_stages * a_stage + kp.b_stages * b_stage;
+  const size_t smem = fixed_smem(bn, d) + kp.a_stages * a_stage + kp.b_stages * b_stage;
   // 128-row blocks -> (128*cg)-row tiles; a pair whose second half lies past the end loads zeros and stores nothing
   kp.num_m_blocks = (kp.num_m_blocks + cg - 1) / cg;
   const int tiles = kp.num_m_blocks * kp.num_n_blocks;

@@ -8,6 +8,9 @@ last consumer has been issued).  Replaying a plan costs one ctypes call per kern
     weight_prep (1 launch, all tensors)  ->  stem_pack  ->  conv1 (im2col GEMM, +BN sums)  ->  bn+relu+maxpool
     -> per residual block:  conv (+sums) -> bn_apply(+relu) ... -> bn_apply(+residual, +relu)
     -> last block: bn_final_pool (relu(bn+residual) -> NCHW spatial features + global average pool)
+  eval mode (running statistics known up front): BatchNorm scale/shift (+residual) + ReLU are folded into the producing
+  convolution's epilogue, which writes the fp16 planes directly - no bn_apply pass at all (resnet.py:76-92,117-137);
+  train mode can use the same epilogue as the second half of a statistics-pass + recompute-pass scheme (two_pass).
 
 Reference arithmetic being reproduced: models/building_blocks/resnet.py:76-92 (BasicBlock), :117-137 (Bottleneck),
 :231-247 (stem + layers) as reached through backbone_models.py:39-54.  Activations live in HBM as NHWC fp16
@@ -180,7 +183,9 @@ class EncoderRunner:
         import os
         self.halo_mode = int(os.environ.get("VINCE_B200_HALO", "-1"))   # -1 auto, 0 off, 1 force (3x3 stride-1 convs)
         # train mode: statistics pass + recompute pass for the wide 1x1 expansions (0 = always raw + bn_apply)
-        self.two_pass = int(os.environ.get("VINCE_B200_TWOPASS", "1"))
+        # (measured on B200, profiles/r02_summary.md: bit-identical results but 5 % slower on ResNet-50 - the expansions
+        #  are bound by the epilogue's shared-memory traffic, not by the HBM write, so it is off by default)
+        self.two_pass = int(os.environ.get("VINCE_B200_TWOPASS", "0"))
         # eval mode: BatchNorm(+residual)+ReLU folded into the producing convolution's epilogue (0 = separate bn_apply)
         self.fold_eval = int(os.environ.get("VINCE_B200_FOLD_EVAL", "1"))
 
@@ -346,22 +351,18 @@ class EncoderRunner:
                                   keep=(raw, raw_ds, act))
                 plan.out_shape = (N, spec.Cout, p_, q_)
                 break
-            raw_ds = ident = None
+            raw_ds = None
             if down is None:
                 res = dict(res_planes=(act.hi, act.lo))
-            elif not train and self.fold_eval:
-                # eval: the downsample branch's BatchNorm is folded into its own epilogue -> identity planes
-                ident, _, _ = self._build_conv_planes(arena, act, down, work, train, launches, relu=False)
-                res = dict(res_planes=(ident.hi, ident.lo))
             else:
+                # downsample branch: raw fp32 output; its BatchNorm is applied where the residual is added (the apply
+                # epilogue of the main convolution, or vince_bn_apply) - same bytes as identity planes, exact fp32 add
                 raw_ds, _, _ = self._build_conv(arena, act, down, work, train, launches)
                 res = dict(res_side=(raw_ds, self._coef(down, work)))
             nxt, p_, q_ = self._build_conv_planes(arena, cur, spec, work, train, launches, relu=True, **res)
             if cur is not act:
                 arena.free(cur.hi, cur.lo)
             arena.free(raw_ds, act.hi, act.lo)
-            if ident is not None:
-                arena.free(ident.hi, ident.lo)
             act = nxt
         plan.launches = launches
         plan.arena_bytes = arena.total
