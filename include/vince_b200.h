@@ -231,6 +231,14 @@ int vince_ema_enqueue(const vince_ema_chunk* table_dev, int32_t n_chunks, float 
                       float* queue, float* queue_tf32, const float* keys, int64_t n0, int64_t dst0, int64_t n1,
                       int64_t dst1, int64_t src1, void* stream);
 
+/* ---- eval: exact k-nearest-neighbour label voting over embeddings ------------------------------------------------
+ * replaces: the kNN-CIFAR evaluation of solvers/vince_solver.py:651-693 (sklearn KDTree(all_features).query(k=11) on
+ * the host, first (self) match dropped, scipy.stats.mode over the neighbour labels).  feats [n,D] fp32 (D % 4 == 0),
+ * labels [n] int64; outputs nbr_idx [n,k], nbr_dist [n,k] (may be NULL), pred [n] (may be NULL; most frequent label,
+ * the smallest one on ties).  k in {1, 3, 5, 10, 15}. */
+int vince_knn_classify(const float* feats, const int64_t* labels, int32_t n, int32_t D, int32_t k, int64_t* nbr_idx,
+                       float* nbr_dist, int64_t* pred, void* stream);
+
 /* ---- multi-GPU: NCCL all-gather of the keys straight into the ring buffer -------------------------------------
  * replaces: the implicit nn.DataParallel gather of vince_model.py:35,125 + StorageQueue.enqueue; one process per
  * GPU.  `unique_id` is the 128-byte ncclUniqueId produced by vince_comm_unique_id on rank 0 and broadcast by the

@@ -80,6 +80,47 @@ def step_parity(rank, world, dev, gather):
     return ok
 
 
+def shuffle_bn_parity(rank, world, dev):
+    """Cross-GPU shuffle-BN: with CrossGpuShuffle the batch shuffle spans the global batch, as
+    nn.DataParallel's split of the shuffled batch does in the reference (vince_model.py:137-142 + :35).  Oracle: the
+    global batch permuted by the same shared-seed permutation, cut into `world` slices, each slice forwarded with its own
+    train-mode BatchNorm statistics, outputs un-shuffled."""
+    import types
+    from vince_b200.distributed import CrossGpuShuffle
+    B, D, H = 8, 128, 64
+    args = types.SimpleNamespace(
+        backbone=vince_b200.ResNet18, num_frames=2, use_attention=False, feature_extractor_gpu_ids=[dev],
+        pytorch_gpu_ids=[dev], vince_embedding_size=D, vince_queue_size=64, vince_temperature=0.07,
+        vince_self_temperature=0.03, vince_momentum=0.999, jigsaw=False, inter_batch_comparison=True,
+        self_batch_comparison=False, batch_size=B, use_imagenet=False)
+    sd = vo.make_state_dict("ResNet18", D, seed=1)
+    model = vince_b200.VinceModel(args)
+    model.load_state_dict(sd)
+    model.to(dev)
+    model.train()
+    model.cross_shuffle = CrossGpuShuffle(seed=99)
+    datas = [torch.randn((B, 3, H, H), generator=torch.Generator().manual_seed(500 + r)) for r in range(world)]
+    out = model.get_embeddings({"data": datas[rank].to(dev)}, shuffle=True)
+    torch.cuda.synchronize()
+    perm = torch.randperm(world * B, generator=torch.Generator().manual_seed(99))
+    glob = torch.cat(datas)
+    expect = torch.empty((world * B, D))
+    with torch.no_grad():
+        for d in range(world):
+            sl = perm[d * B:(d + 1) * B]
+            expect[sl] = vo.get_embeddings(glob[sl], vo.clone_state_dict(sd), "ResNet18", True)["embeddings"]
+    mine = expect[rank * B:(rank + 1) * B]
+    err = ((out["embeddings"].cpu() - mine).norm() / mine.norm()).item()
+    # and it must differ from the purely local shuffle (different BatchNorm batches)
+    with torch.no_grad():
+        local = vo.get_embeddings(datas[rank], vo.clone_state_dict(sd), "ResNet18", True)["embeddings"]
+    differs = ((local - mine).norm() / mine.norm()).item()
+    if rank == 0 or err >= 1e-3:
+        print("rank %d cross-GPU shuffle-BN: embeddings rel-L2 %.2e vs the global-shuffle oracle (local-BN result is %.2e away)"
+              % (rank, err, differs))
+    return err < 1e-3 and differs > 1e-2
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dev = "cuda:%d" % local
@@ -108,6 +149,7 @@ def main():
         vince_b200.ops.round_tf32(queue.vector_queue, shadow)
         ok = ok and torch.equal(shadow, queue.vector_queue_tf32)
     ok = step_parity(rank, world, dev, gather) and ok
+    ok = shuffle_bn_parity(rank, world, dev) and ok
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -577,6 +577,42 @@ def test_loss_backward_fails_loudly_or_trains():
         assert not model.loss(out)["nce_loss"][1].requires_grad
 
 
+def test_knn_matches_sklearn_kdtree():
+    """vince_solver.py:651-693: KDTree(features).query(k=11), drop self, mode of the neighbour labels, accuracy."""
+    import scipy.stats
+    from sklearn.neighbors import KDTree
+    from vince_b200 import knn
+    gen = torch.Generator().manual_seed(12)
+    n, D, C = 3001, 128, 10
+    centers = F.normalize(torch.randn((C, D), generator=gen), dim=1)
+    labels = torch.randint(0, C, (n,), generator=gen)
+    feats = F.normalize(centers[labels] + 0.35 * torch.randn((n, D), generator=gen), dim=1)
+    nbr, dist, pred = knn.knn_classify(feats.to(DEV), labels.to(DEV), k=10)
+    torch.cuda.synchronize()
+    kdt = KDTree(feats.numpy(), leaf_size=40, metric="euclidean")
+    ref_d, ref_i = kdt.query(feats.numpy(), k=11)
+    ref_i, ref_d = ref_i[:, 1:], ref_d[:, 1:]
+    ref_pred = scipy.stats.mode(labels.numpy()[ref_i], axis=1)[0].reshape(-1)
+    ref_acc = float(np.mean(ref_pred == labels.numpy()))
+    same_sets = np.mean([set(a) == set(b) for a, b in zip(nbr.cpu().numpy(), ref_i)])
+    assert same_sets > 0.999, same_sets                         # fp32 vs fp64 distances may swap exact near-ties
+    np.testing.assert_allclose(dist.cpu().numpy(), ref_d, rtol=1e-4, atol=1e-6)
+    agree = float((pred.cpu().numpy() == ref_pred).mean())
+    acc = float(knn.knn_accuracy(feats.to(DEV), labels.to(DEV), k=10))
+    print("kNN: neighbour sets equal %.4f, predictions agree %.4f, accuracy %.4f (sklearn %.4f)" % (same_sets, agree, acc, ref_acc))
+    assert agree > 0.999 and abs(acc - ref_acc) < 2e-3
+    # end to end through the eval-mode encoder (folded BatchNorm), uint8 frames and the reference's float dataset tensor
+    args, model, sd = build_model("ResNet18", 4, 64, 64, 128, seed=3)
+    model.eval()
+    imgs8 = torch.randint(0, 256, (96, 32, 32, 3), generator=gen, dtype=torch.uint8)
+    labs = torch.randint(0, 10, (96,), generator=gen)
+    acc8, feats8 = knn.knn_eval(model, imgs8, labs.to(DEV), batch_size=40)
+    accf, featsf = knn.knn_eval(model, imgs8.permute(0, 3, 1, 2).float() / 255.0, labs.to(DEV), batch_size=40)
+    torch.cuda.synchronize()
+    assert feats8.shape == (96, 128) and 0.0 <= float(acc8) <= 1.0
+    assert rel(feats8, featsf) < 1e-5
+
+
 def test_multi_gpu_allgather_and_shard_parity():
     """Collected multi-GPU parity: skips below 2 visible GPUs; otherwise launches
     tests/multigpu_check.py under torchrun on every visible GPU (bit-exact all-gather + enqueue vs the oracle's

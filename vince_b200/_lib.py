@@ -76,6 +76,8 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vince_ema_enqueue": (c_int32, [c_void_p, c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int64,
                                     c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "vince_knn_classify": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                     c_void_p]),
     "vince_comm_unique_id": (c_int32, [c_void_p]),
     "vince_comm_init": (c_int32, [POINTER(c_void_p), c_void_p, c_int32, c_int32]),
     "vince_comm_destroy": (c_int32, [c_void_p]),

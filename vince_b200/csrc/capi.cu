@@ -206,6 +206,13 @@ int vince_ema_enqueue(const vince_ema_chunk* table_dev, int32_t n_chunks, float 
                             queue_tf32, keys, n0, dst0, n1, dst1, src1, S(stream));
 }
 
+int vince_knn_classify(const float* feats, const int64_t* labels, int32_t n, int32_t D, int32_t k, int64_t* nbr_idx,
+                       float* nbr_dist, int64_t* pred, void* stream) {
+  VB_REQUIRE(feats && nbr_idx, "vince_knn_classify: null pointer");
+  VB_REQUIRE(!pred || labels, "vince_knn_classify: predictions need labels");
+  return knn_launch(feats, labels, n, D, k, nbr_idx, nbr_dist, pred, S(stream));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // NCCL (bound lazily)
 // ---------------------------------------------------------------------------------------------------------------

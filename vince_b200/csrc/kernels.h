@@ -148,4 +148,10 @@ int masked_ce_launch(const float* sims, const uint8_t* mask, int R, int C, int n
                      float* weights, float* pos_sim, float* neg_max, float* row_lse, float* scalars, int* error_flag,
                      cudaStream_t stream);
 
+// ---- knn.cu ------------------------------------------------------------------------------------------------
+// exact k-NN of every row of feats [n, D] among all rows (Euclidean), self match dropped; nbr_idx [n, k],
+// nbr_dist [n, k] (optional), pred [n] = most frequent neighbour label (smallest on ties; optional with labels)
+int knn_launch(const float* feats, const int64_t* labels, int n, int D, int k, int64_t* nbr_idx, float* nbr_dist,
+               int64_t* pred, cudaStream_t stream);
+
 }  // namespace vb

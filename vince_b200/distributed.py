@@ -84,3 +84,73 @@ class KeyGather:
         if self.comm:
             _lib.lib().vince_comm_destroy(self.comm)
             self.comm = ctypes.c_void_p()
+
+
+class CrossGpuShuffle:
+    """MoCo's cross-GPU batch shuffle ("shuffle-BN") for one-process-per-GPU training.
+
+    The reference shuffles the batch with ONE global randperm and lets nn.DataParallel split the shuffled batch
+    across the GPUs (models/vince_model.py:137-142 + :35,125), so every GPU's train-mode BatchNorm normalises a random
+    mix of clips and the key encoder cannot read "which frames belong together" off the batch statistics; the outputs
+    are un-shuffled afterwards (:184-192).  With one process per GPU that is a permutation of the GLOBAL batch of
+    world x B frames: rank r forwards frames perm[r*B:(r+1)*B], wherever they live.
+
+    Every rank draws the same permutation from a shared-seed CPU generator (no communication), so all (source,
+    destination) counts are known everywhere and the exchange is one variable-split all-to-all of the frames (NCCL over
+    NVLink; 1 byte/pixel with uint8 frames) before the forward and one all-to-all of each [B, ...] output back.
+    `exchange(x)` -> (x_shuffled, ctx); `restore(y, ctx)` returns rows to their owner, in original order.
+    """
+
+    def __init__(self, group=None, seed=0):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.gen = torch.Generator().manual_seed(seed)         # identical stream on every rank
+
+    @staticmethod
+    def plan(perm, world, rank, B):
+        """Pure index arithmetic (tested on CPU).  perm: global permutation [world*B]; rank r forwards frames
+        perm[r*B:(r+1)*B].  Returns (send_order [B] local indices grouped by destination, send_counts [world],
+        recv_counts [world], place [B]: received row i (grouped by source, then by position in the source's send order)
+        is row place[i] of this rank's shuffled batch)."""
+        perm = perm.to(torch.int64)
+        n = world * B
+        pos_of = torch.empty(n, dtype=torch.int64)
+        pos_of[perm] = torch.arange(n, dtype=torch.int64)       # global frame g sits at position pos_of[g] of the shuffle
+        mine = torch.arange(rank * B, (rank + 1) * B, dtype=torch.int64)
+        pos = pos_of[mine]                                      # where my frames go
+        order = torch.argsort(pos)                              # by destination rank, then by position there
+        send_order = order
+        send_counts = torch.bincount(pos // B, minlength=world)
+        want = perm[rank * B:(rank + 1) * B]                    # the frames I forward, in shuffled order
+        src = want // B
+        recv_counts = torch.bincount(src, minlength=world)
+        # rows arrive grouped by source; within a source in increasing shuffled position (the sender's order)
+        place = torch.argsort(src, stable=True)
+        return send_order, send_counts.tolist(), recv_counts.tolist(), place
+
+    def _a2a(self, x, in_splits, out_splits):
+        out = torch.empty((sum(out_splits),) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        self.dist.all_to_all_single(out, x.contiguous(), output_split_sizes=out_splits, input_split_sizes=in_splits,
+                                    group=self.group)
+        return out
+
+    def exchange(self, x):
+        """x: [B, ...] this rank's frames.  Returns (shuffled local batch [B, ...], ctx)."""
+        B = x.shape[0]
+        perm = torch.randperm(self.world * B, generator=self.gen)
+        send_order, send_counts, recv_counts, place = self.plan(perm, self.world, self.rank, B)
+        dev = x.device
+        send_order_d, place_d = send_order.to(dev), place.to(dev)
+        got = self._a2a(x.index_select(0, send_order_d), send_counts, recv_counts)
+        shuffled = torch.empty_like(got)
+        shuffled.index_copy_(0, place_d, got)
+        return shuffled, (send_order_d, send_counts, recv_counts, place_d, perm)
+
+    def restore(self, y, ctx):
+        """y: [B, ...] outputs for the shuffled batch.  Returns the outputs of THIS rank's own frames, original order."""
+        send_order_d, send_counts, recv_counts, place_d, _ = ctx
+        back = self._a2a(y.index_select(0, place_d), recv_counts, send_counts)
+        out = torch.empty_like(back)
+        out.index_copy_(0, send_order_d, back)
+        return out

@@ -362,6 +362,9 @@ class VinceModel(BaseModel):
 
     def _get_embeddings(self, inputs, jigsaw, shuffle, jigsaw_orders):
         self.launches = 0
+        cross = getattr(self, "cross_shuffle", None) if shuffle else None
+        if cross is not None:
+            return self._get_embeddings_cross_shuffled(inputs, jigsaw, jigsaw_orders, cross)
         with torch.no_grad():
             data = inputs["data"]
             n = data.shape[0]
@@ -390,6 +393,27 @@ class VinceModel(BaseModel):
         if "batch_types" in inputs:
             return_val = self.split_dict_by_type(inputs["batch_types"], inputs["batch_sizes"], return_val)
         return return_val
+
+    def _get_embeddings_cross_shuffled(self, inputs, jigsaw, jigsaw_orders, cross):
+        """shuffle=True with `self.cross_shuffle` (vince_b200.distributed.CrossGpuShuffle) set: the batch shuffle of
+        vince_model.py:137-142 spans the GLOBAL batch of all ranks, as it does in the reference where nn.DataParallel
+        splits the shuffled batch across the GPUs - frames travel to the rank that forwards them (one all-to-all),
+        BatchNorm sees a random mix of clips, and every [B, ...] output travels back to its owner (:184-192)."""
+        with torch.no_grad():
+            data = inputs["data"]
+            shuffled, ctx = cross.exchange(data)
+            sub = {"data": shuffled}
+            out = self._get_embeddings(sub, jigsaw, False, jigsaw_orders)
+            n = data.shape[0]
+            back = {}
+            for key, val in out.items():
+                if isinstance(val, torch.Tensor) and val.shape[0] == n:
+                    back[key] = cross.restore(val, ctx)
+                else:
+                    back[key] = val
+        if "batch_types" in inputs:
+            back = self.split_dict_by_type(inputs["batch_types"], inputs["batch_sizes"], back)
+        return back
 
     def _jigsaw_embeddings(self, data, shuffle_order, jigsaw_orders):
         # vince_model.py:144-173.  On one device the batch shuffle only permutes rows, so instead of gathering the
