@@ -215,10 +215,20 @@ class HotPath:
             os.sched_setaffinity(0, old_aff)
         self.devbuf = {k: (v[0].to(dev), v[1].to(dev)) for k, v in self.host.items()}
         self.coin = random.Random(2020 + rank)
+        self.opt = None
         self.launches = 0
         self.prefetch = None
 
-    def step(self, data, queue_data):
+    def step(self, data, queue_data, train=False):
+        """train=False: the forward-only scoring step (under no_grad, like the CPU arm).  train=True: the whole
+        run_train_iteration - the same forward with the backward tape, loss.backward() through the sm_100a backward
+        kernels, the fused SGD step, then enqueue + EMA (vince_solver.py:397-499)."""
+        if not train:
+            with self.torch.no_grad():
+                return self._step(data, queue_data, False)
+        return self._step(data, queue_data, True)
+
+    def _step(self, data, queue_data, train):
         wl = self.wl
         batch = {"data": data, "queue_data": queue_data, "batch_types": ["images"], "batch_sizes": [wl["B"]],
                  "data_source": "synthetic", "num_frames": wl["nf"]}
@@ -238,9 +248,18 @@ class HotPath:
         output.update(queue_batches[0])
         self.model.launches = 0
         output.update(self.model(output))                                             # :424
-        loss = self.model.loss(output)["nce_loss"][1]                                 # :425
+        loss_pair = self.model.loss(output)["nce_loss"]                               # :425
+        loss = loss_pair[1]
         self.model.get_metrics(output)                                                # :426
         launches += self.model.launches
+        if train:                                                                     # :463-469
+            if self.opt is None:
+                from vince_b200.optim import FusedSGD
+                self.opt = FusedSGD(self.model.parameters(), lr=0.03, momentum=0.9, weight_decay=1e-4)
+            self.opt.zero_grad()
+            (loss_pair[0] * loss).backward()
+            self.opt.step()
+            launches += getattr(self.model, "backward_launches", 0) + 1
         keys = output["queue_embeddings"]
         # :497-499 (N>1: the key all-gather, the ring-buffer scatter and the EMA share one call / one kernel)
         self.qm.vince_update(self.model, enqueue=(self.queue, keys, [None] * wl["B"], "synthetic"), gather=self.gather)
@@ -378,6 +397,25 @@ def run_ours(a):
         nce_step(True)
     nce_ms = timed(nce_step, 20) / 20
     nce_bwd_ms = timed(lambda: nce_step(True), 20) / 20
+    # ---- full training step (forward with tape + backward + fused SGD + enqueue + EMA), device resident ----
+    train = None
+    if not wl["jigsaw"] and not a.no_train:
+        try:
+            t_steps = max(3, min(a.steps, 10))
+            for _ in range(2):
+                hp.step(data, queue_data, train=True)
+            t_ms = timed(lambda: hp.step(data, queue_data, train=True), t_steps)
+            train = {"ms_per_step": round(t_ms / t_steps, 4), "value": round(frames_per_step * t_steps / (t_ms / 1e3), 1),
+                     "unit": "frames/s", "steps": t_steps, "gpu_launches_per_step": hp.launches,
+                     "what": "whole run_train_iteration (vince_solver.py:397-499): both encoder forwards, fused InfoNCE, "
+                             "loss.backward() through the sm_100a dgrad / wgrad / BatchNorm-backward kernels, fused "
+                             "momentum-SGD, enqueue + EMA; device-resident inputs; gradients are NOT all-reduced in "
+                             "this leg"}
+            hp.opt.zero_grad()
+            hp.model.feature_extractor.module.runner._plans.clear()       # drop the taped plan's activations
+            hp.step(data, queue_data)
+        except Exception as e:  # noqa: BLE001  (the forward-only metric must survive a failing extra leg)
+            train = {"error": str(e)[:300]}
     # ---- end-to-end leg: host (pinned) inputs, H2D inside the timed region, loss read back every step ----
     hp.run_e2e(3, kind)
     e2e_steps = a.steps
@@ -461,6 +499,7 @@ def run_ours(a):
         "infonce_step_with_dq_backward_ms": round(nce_bwd_ms, 4),
         "infonce_step_what": "similarity+CE+metrics + %sEMA + enqueue, device resident, B=%d K=%d D=%d" % (
             "key all-gather + " if world > 1 else "", wl["B"], wl["K"], wl["D"]),
+        "train_step": train,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "ms_per_step": round(e2e_ms / e2e_steps, 4),
                 "h2d_bytes_per_step": h2d_main, "d2h_bytes_per_step": 4, "steps": e2e_steps,
@@ -659,6 +698,7 @@ def main():
     ap.add_argument("--input", default="uint8", choices=["fp32", "uint8"],
                     help="uint8 = raw HWC frames, normalisation fused into the stem packing (default: the format the "
                          "reference's workers hold); fp32 = the reference's normalised NCHW tensors")
+    ap.add_argument("--no-train", action="store_true", help="skip the extra full-training-step leg")
     ap.add_argument("--profile-only", action="store_true",
                     help="stop after the device-resident timed steps (for runs under ncu; prints no bench value)")
     a = ap.parse_args()

@@ -98,6 +98,17 @@ typedef struct {
   const void* res_lo;
   const float* res_raw;
   const float* res_coef;
+  /* training support (ABI v3) */
+  int32_t bn_save;        /* 1: the fused finalize also stores the batch mean and 1/sqrt(var+eps): bn_coef is [4][N]
+                           * (scale, shift, mean, inv-std) - what the BatchNorm backward needs */
+  int32_t kchunk;         /* > 0: batched split-K GEMM for weight gradients (replaces autograd's conv2d / linear weight
+                           * gradient at vince_solver.py:465): out[(tap*splits+split)*Mpad + m, n] = sum over the split's
+                           * k of A[m,k] * B[n, k + shift(tap)]; K = whole contraction extent (pixels), kchunk = k per
+                           * split (multiple of 64), Mpad = M rounded up to 128, splits = ceil(K / kchunk) */
+  int32_t taps;           /* 1, or 9 with shift(tap) = (tap/3 - 1)*shift_w + tap%3 - 1 (3x3 filter taps as shifts along
+                           * a zero-padded pixel axis of row pitch shift_w) */
+  int32_t shift_w;
+  const float* alpha_dev; /* optional DEVICE scalar multiplied into alpha (dynamic power-of-two gradient scaling) */
 } vince_conv_desc;
 int vince_conv_fwd(const vince_conv_desc* desc, void* stream);
 /* eval-mode BatchNorm coefficients from the running statistics: coef[2][C] */
@@ -231,6 +242,74 @@ int vince_ema_enqueue(const vince_ema_chunk* table_dev, int32_t n_chunks, float 
                       float* queue, float* queue_tf32, const float* keys, int64_t n0, int64_t dst0, int64_t n1,
                       int64_t dst1, int64_t src1, void* stream);
 
+/* ---- query-encoder backward + optimiser ---------------------------------------------------
+ * replaces: what torch autograd + torch.optim.SGD do for the query encoder at solvers/vince_solver.py:252-256,463-469
+ *           (loss.backward(); optimizer.step()).  The contractions run on vince_conv_fwd:
+ *   data gradient    dX = conv_stride1(dilate(dRaw), W')   with W' from vince_weight_prep kind = 2 (flipped, channel-
+ *                    transposed filter), alpha_dev = the 2^-e of the dRaw planes;
+ *   weight gradient  batched split-K GEMM (kchunk / taps / shift_w) between vince_transpose_pad'ed dRaw and input planes,
+ *                    reduced by vince_wgrad_reduce into the OIHW fp32 gradient.
+ * vince_bn_bwd handles one conv + BatchNorm (+ residual) (+ ReLU) unit (train-mode batch statistics, resnet.py:76-92,
+ * 117-137): dZ = (dA + dB) masked by the ReLU; d gamma = sum dZ*xhat, d beta = sum dZ;
+ * dRaw = gamma*invstd*(dZ - mean dZ - xhat * mean(dZ*xhat)) written as fp16 planes scaled by a power of two 2^e chosen
+ * per unit (kept at work + 3C as two floats 2^e, 2^-e), optionally zero-dilated for stride-2 convolutions. */
+typedef struct {
+  const float* dA;          /* [M,C] gradient wrt the unit's output ([M/bcast_hw, C] if bcast_hw > 0: avg-pool backward) */
+  const float* dB;          /* optional second addend */
+  int32_t bcast_hw;
+  int32_t mask_kind;        /* 0 none, 1 relu(raw*scale+shift) > 0 recomputed, 2 saved output planes > 0 */
+  const void* out_hi;
+  const void* out_lo;
+  const float* raw;         /* [M,C] raw conv output */
+  const float* coef;        /* [4][C] scale, shift, mean, inv-std (vince_conv_fwd with bn_save = 1) */
+  int64_t M;
+  int32_t C;
+  double* work;             /* (3C + 2) doubles */
+  float* dgamma;            /* optional [C] */
+  float* dbeta;
+  int32_t accumulate;
+  void* d_hi;               /* optional: planes of 2^e * dRaw, [M,C] or dilated [N,Hd,Wd,C] (pre-zeroed) */
+  void* d_lo;
+  float* d_f32;             /* optional: fp32 dRaw */
+  float* dz_out;            /* optional: masked dZ (gradient of the skip path) */
+  int32_t dil, P, Q, Hd, Wd;
+} vince_bn_bwd_desc;
+int vince_bn_bwd(const vince_bn_bwd_desc* desc, void* stream);
+/* planes [N*P*Q, C] -> [copies*C][ld] planes, (n,p,q,c) at column n*Hp*Wp + (p*stride+offset)*Wp + q*stride+offset;
+ * copies = 3 additionally stores the tensor shifted by -1 / 0 / +1 columns in rows [0,C) / [C,2C) / [2C,3C) (TMA needs
+ * 16-byte aligned addresses: the 3x3 taps' column shifts are realised by picking a copy) */
+int vince_transpose_pad(const void* src_hi, const void* src_lo, void* dst_hi, void* dst_lo, int64_t M, int32_t C, int32_t P,
+                        int32_t Q, int32_t stride, int32_t offset, int32_t Hp, int32_t Wp, int64_t ld, int32_t copies,
+                        void* stream);
+/* partials [taps*splits][Mpad][Cin] -> grad [Cout][Cin][taps] (OIHW), times scale * (*scale_dev) */
+int vince_wgrad_reduce(const float* partials, int32_t taps, int32_t splits, int32_t Mpad, int32_t Cout, int32_t Cin,
+                       const float* scale_dev, float scale, float* grad, int32_t accumulate, void* stream);
+/* max-pool 3x3/2 backward through relu(bn(raw)) of the stem (resnet.py:173,236): dst [N,P,Q,C] fp32 */
+int vince_maxpool_bwd(const float* dA, const float* dB, const float* raw, const float* coef, float* dst, int32_t N,
+                      int32_t P, int32_t Q, int32_t C, void* stream);
+/* conv1 (7x7/2, Cin = 3) weight gradient from the fp32 dRaw [N,P,Q,64] and the input frames (fp32 NCHW or uint8 HWC) */
+int vince_stem_wgrad(const float* x, const uint8_t* x_u8, const int64_t* gather_idx, const float* mean3,
+                     const float* std3, const float* draw, float* grad, int32_t N, int32_t H, int32_t W,
+                     int32_t accumulate, void* stream);
+/* projection head: fp32 GEMM C (+)= op(A) op(B), optional ReLU mask (zero where relu_mask_src <= 0); column sums;
+ * F.normalize backward (vince_model.py:177-180) */
+int vince_sgemm(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t lda, int32_t ldb,
+                int32_t ldc, int32_t trans_a, int32_t trans_b, int32_t accumulate, const float* relu_mask_src,
+                void* stream);
+int vince_colsum(const float* x, float* out, int32_t R, int32_t C, int32_t accumulate, void* stream);
+int vince_normalize_bwd(const float* x, const float* dy, float* dx, int32_t rows, int32_t D, float eps, float gscale,
+                        void* stream);
+/* fused multi-tensor SGD, torch.optim.SGD semantics (vince_solver.py:252-256): d = g*grad_scale + wd*p;
+ * buf = first_step ? d : momentum*buf + d; p -= lr*buf */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* buf;
+  int64_t count;
+} vince_sgd_chunk;
+int vince_sgd_step(const vince_sgd_chunk* table_dev, int32_t n_chunks, float lr, float momentum, float weight_decay,
+                   float grad_scale, int32_t first_step, void* stream);
+
 /* ---- eval: exact k-nearest-neighbour label voting over embeddings ------------------------------------------------
  * replaces: the kNN-CIFAR evaluation of solvers/vince_solver.py:651-693 (sklearn KDTree(all_features).query(k=11) on
  * the host, first (self) match dropped, scipy.stats.mode over the neighbour labels).  feats [n,D] fp32 (D % 4 == 0),
@@ -255,6 +334,10 @@ int vince_allgather_enqueue_ema(void* comm, const float* keys, int64_t n_local, 
                                 float* queue_tf32, int64_t K, int64_t tail, float* scratch,
                                 const vince_ema_chunk* table_dev, int32_t n_chunks, float momentum,
                                 float one_minus_momentum, void* stream);
+
+/* in-place sum all-reduce of the flat gradient buffer over the communicator of vince_comm_init (data-parallel training:
+ * replaces the gradient reduction nn.DataParallel performs on GPU 0) */
+int vince_allreduce_sum(void* comm, float* buf, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,11 +26,22 @@ class ConvDesc(Structure):
         ("alpha", c_float), ("stats_only", c_int32),
         ("out_hi", c_void_p), ("out_lo", c_void_p), ("ep_coef", c_void_p), ("res_kind", c_int32), ("reserved", c_int32),
         ("res_hi", c_void_p), ("res_lo", c_void_p), ("res_raw", c_void_p), ("res_coef", c_void_p),
+        ("bn_save", c_int32), ("kchunk", c_int32), ("taps", c_int32), ("shift_w", c_int32), ("alpha_dev", c_void_p),
     ]
 
 
 class BnSide(Structure):
     _fields_ = [("raw", c_void_p), ("coef", c_void_p)]
+
+
+class BnBwdDesc(Structure):
+    _fields_ = [
+        ("dA", c_void_p), ("dB", c_void_p), ("bcast_hw", c_int32), ("mask_kind", c_int32),
+        ("out_hi", c_void_p), ("out_lo", c_void_p), ("raw", c_void_p), ("coef", c_void_p),
+        ("M", c_int64), ("C", c_int32), ("work", c_void_p), ("dgamma", c_void_p), ("dbeta", c_void_p),
+        ("accumulate", c_int32), ("d_hi", c_void_p), ("d_lo", c_void_p), ("d_f32", c_void_p), ("dz_out", c_void_p),
+        ("dil", c_int32), ("P", c_int32), ("Q", c_int32), ("Hd", c_int32), ("Wd", c_int32),
+    ]
 
 
 class InfoNceDesc(Structure):
@@ -76,6 +87,21 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vince_ema_enqueue": (c_int32, [c_void_p, c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int64,
                                     c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "vince_bn_bwd": (c_int32, [POINTER(BnBwdDesc), c_void_p]),
+    "vince_transpose_pad": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
+                                      c_int32, c_int32, c_int32, c_int64, c_int32, c_void_p]),
+    "vince_wgrad_reduce": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_float, c_void_p,
+                                     c_int32, c_void_p]),
+    "vince_maxpool_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                    c_void_p]),
+    "vince_stem_wgrad": (c_int32, [c_void_p, c_void_p, c_void_p, POINTER(c_float), POINTER(c_float), c_void_p, c_void_p,
+                                   c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "vince_sgemm": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                              c_int32, c_int32, c_void_p, c_void_p]),
+    "vince_colsum": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "vince_normalize_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_float, c_void_p]),
+    "vince_sgd_step": (c_int32, [c_void_p, c_int32, c_float, c_float, c_float, c_float, c_int32, c_void_p]),
+    "vince_allreduce_sum": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
     "vince_knn_classify": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                      c_void_p]),
     "vince_comm_unique_id": (c_int32, [c_void_p]),

@@ -103,14 +103,15 @@ class Backbone(nn.Module):
         self.output_channels = self.model.output_channels
         self.runner = EncoderRunner(self.model, passes=getattr(args, "vince_b200_passes", 3))
 
-    def forward(self, x, final_layer=None, gather_idx=None, scatter_idx=None, want_pooled=False, patch_grid=1):
+    def forward(self, x, final_layer=None, gather_idx=None, scatter_idx=None, want_pooled=False, patch_grid=1,
+                tape=False):
         """x: NCHW fp32 CUDA tensor.  Returns NCHW spatial features [B, C, h, w] (and the global-average-pooled
         [B, C] when want_pooled).  gather_idx / scatter_idx fold the MoCo batch shuffle / un-shuffle
         (vince_model.py:137-142,184-192) into the first load and the last store."""
         if final_layer is not None and final_layer != self.final_layer and final_layer != -2:
             raise NotImplementedError("vince_b200.Backbone: only final_layer=-2 is implemented")
         spatial, pooled = self.runner.forward(x, train=self.training, gather_idx=gather_idx, scatter_idx=scatter_idx,
-                                              patch_grid=patch_grid)
+                                              patch_grid=patch_grid, tape=tape)
         return (spatial, pooled) if want_pooled else spatial
 
 

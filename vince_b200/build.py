@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libvince_b200.so")
-SOURCES = ["host.cu", "conv_gemm.cu", "elementwise.cu", "infonce.cu", "infonce_bwd.cu", "knn.cu", "capi.cu"]
+SOURCES = ["host.cu", "conv_gemm.cu", "elementwise.cu", "infonce.cu", "infonce_bwd.cu", "knn.cu", "backward.cu", "capi.cu"]
 HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "vince_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

@@ -30,7 +30,7 @@ static int check_side(const vince_bn_side* s, const char* what) {
 extern "C" {
 
 const char* vince_last_error(void) { return get_error(); }
-int vince_abi_version(void) { return 2; }
+int vince_abi_version(void) { return 3; }
 
 int vince_conv_fwd(const vince_conv_desc* d, void* stream) {
   VB_REQUIRE(d != nullptr, "vince_conv_fwd: null descriptor");
@@ -51,6 +51,8 @@ int vince_conv_fwd(const vince_conv_desc* d, void* stream) {
   g.out_hi = d->out_hi, g.out_lo = d->out_lo, g.ep_coef = d->ep_coef, g.res_kind = d->res_kind;
   g.res_hi = d->res_hi, g.res_lo = d->res_lo, g.res_raw = d->res_raw, g.res_coef = d->res_coef;
   g.stats_only = d->stats_only;
+  g.bn_save = d->bn_save, g.alpha_dev = d->alpha_dev;
+  g.kchunk = d->kchunk, g.taps = d->taps, g.shift_w = d->shift_w;
   g.trace = getenv("VINCE_B200_TRACE_PTR") ? reinterpret_cast<void*>(strtoull(getenv("VINCE_B200_TRACE_PTR"), nullptr, 0)) : nullptr;
   return conv_gemm_launch(g, S(stream));
 }
@@ -206,6 +208,50 @@ int vince_ema_enqueue(const vince_ema_chunk* table_dev, int32_t n_chunks, float 
                             queue_tf32, keys, n0, dst0, n1, dst1, src1, S(stream));
 }
 
+// ---- query-encoder backward -----------------------------------------------------------------
+int vince_bn_bwd(const vince_bn_bwd_desc* d, void* stream) {
+  VB_REQUIRE(d != nullptr, "vince_bn_bwd: null descriptor");
+  static_assert(sizeof(vince_bn_bwd_desc) == sizeof(BnBwdDesc), "ABI struct mismatch");
+  return bn_bwd_launch(*reinterpret_cast<const BnBwdDesc*>(d), S(stream));
+}
+int vince_transpose_pad(const void* src_hi, const void* src_lo, void* dst_hi, void* dst_lo, int64_t M, int32_t C, int32_t P,
+                        int32_t Q, int32_t stride, int32_t offset, int32_t Hp, int32_t Wp, int64_t ld, int32_t copies,
+                        void* stream) {
+  return transpose_pad_launch(HF(src_hi), HF(src_lo), HF(dst_hi), HF(dst_lo), M, C, P, Q, stride, offset, Hp, Wp, ld,
+                              copies, S(stream));
+}
+int vince_wgrad_reduce(const float* partials, int32_t taps, int32_t splits, int32_t Mpad, int32_t Cout, int32_t Cin,
+                       const float* scale_dev, float scale, float* grad, int32_t accumulate, void* stream) {
+  return wgrad_reduce_launch(partials, taps, splits, Mpad, Cout, Cin, scale_dev, scale, grad, accumulate, S(stream));
+}
+int vince_maxpool_bwd(const float* dA, const float* dB, const float* raw, const float* coef, float* dst, int32_t N,
+                      int32_t P, int32_t Q, int32_t C, void* stream) {
+  return maxpool_bwd_launch(dA, dB, raw, coef, dst, N, P, Q, C, S(stream));
+}
+int vince_stem_wgrad(const float* x, const uint8_t* x_u8, const int64_t* gather_idx, const float* mean3,
+                     const float* std3, const float* draw, float* grad, int32_t N, int32_t H, int32_t W,
+                     int32_t accumulate, void* stream) {
+  return stem_wgrad_launch(x, x_u8, gather_idx, mean3, std3, draw, grad, N, H, W, accumulate, S(stream));
+}
+int vince_sgemm(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t lda, int32_t ldb,
+                int32_t ldc, int32_t trans_a, int32_t trans_b, int32_t accumulate, const float* relu_mask_src,
+                void* stream) {
+  return sgemm_launch(A, B, C, M, N, K, lda, ldb, ldc, trans_a, trans_b, accumulate, relu_mask_src, S(stream));
+}
+int vince_colsum(const float* x, float* out, int32_t R, int32_t C, int32_t accumulate, void* stream) {
+  return colsum_launch(x, out, R, C, accumulate, S(stream));
+}
+int vince_normalize_bwd(const float* x, const float* dy, float* dx, int32_t rows, int32_t D, float eps, float gscale,
+                        void* stream) {
+  return normalize_bwd_launch(x, dy, dx, rows, D, eps, gscale, S(stream));
+}
+int vince_sgd_step(const vince_sgd_chunk* table_dev, int32_t n_chunks, float lr, float momentum, float weight_decay,
+                   float grad_scale, int32_t first_step, void* stream) {
+  static_assert(sizeof(vince_sgd_chunk) == sizeof(SgdChunk), "ABI struct mismatch");
+  return sgd_launch(reinterpret_cast<const SgdChunk*>(table_dev), n_chunks, lr, momentum, weight_decay, grad_scale,
+                    first_step, S(stream));
+}
+
 int vince_knn_classify(const float* feats, const int64_t* labels, int32_t n, int32_t D, int32_t k, int64_t* nbr_idx,
                        float* nbr_dist, int64_t* pred, void* stream) {
   VB_REQUIRE(feats && nbr_idx, "vince_knn_classify: null pointer");
@@ -227,6 +273,7 @@ static struct {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
   ncclResult_t (*CommDestroy)(ncclComm_t);
   ncclResult_t (*AllGather)(const void*, void*, size_t, int /*dtype*/, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int /*dtype*/, int /*op*/, ncclComm_t, cudaStream_t);
   const char* (*GetErrorString)(ncclResult_t);
 } g_nccl;
 
@@ -247,6 +294,7 @@ static int load_nccl() {
   g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
   g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
   g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(dlsym(h, "ncclAllGather"));
+  g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(h, "ncclAllReduce"));
   g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather) {
     set_error("libnccl is missing required symbols");
@@ -338,6 +386,17 @@ int vince_allgather_enqueue_ema(void* comm, const float* keys, int64_t n_local, 
                                 float one_minus_momentum, void* stream) {
   return allgather_enqueue_impl(comm, keys, n_local, D, queue, queue_tf32, K, tail, scratch, table_dev, n_chunks,
                                 momentum, one_minus_momentum, stream);
+}
+
+int vince_allreduce_sum(void* comm, float* buf, int64_t n, void* stream) {
+  VB_REQUIRE(comm && buf && n >= 0, "vince_allreduce_sum: bad argument");
+  int rc = load_nccl();
+  if (rc) return rc;
+  VB_REQUIRE(g_nccl.AllReduce, "libnccl lacks ncclAllReduce");
+  if (n == 0) return VB_OK;
+  // in place, ncclFloat32 == 7, ncclSum == 0
+  VB_CHECK_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, 7, 0, reinterpret_cast<ncclComm_t>(comm), S(stream)));
+  return VB_OK;
 }
 
 }  // extern "C"

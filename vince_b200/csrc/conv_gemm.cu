@@ -51,6 +51,17 @@ struct GemmKernelParams {
   const float* res_raw;
   const float* res_coef;
   int stats_only;                // EPI == 0: accumulate BatchNorm sums / finalize but store nothing
+  // batched split-K GEMM (weight gradients; tiled A mode only): tile -> (batch, m_blk, n_blk), batch -> (tap, split);
+  // A k-offset = split * kchunk; B k-offset = split * kchunk + (tap/3 - 1) * shift_w and B rows (tap%3) * N + n for
+  // taps == 9 (B = three column-shifted copies stacked along the rows); output rows batch * out_batch_rows + m
+  int num_tiles;
+  int tiles_per_batch;           // num_m_blocks * num_n_blocks
+  int splits;                    // k-splits per tap
+  int kchunk;                    // elements of K per split (multiple of 64)
+  int shift_w;                   // padded row pitch of the pixel axis (0: no taps)
+  int out_batch_rows;
+  const float* alpha_dev;        // optional device scalar multiplied into alpha (dynamic power-of-two gradient scale)
+  int bn_save;                   // finalize also writes bn_coef[2N..3N) = mean, [3N..4N) = 1/sqrt(var+eps)
   int M, N;
   int num_m_blocks, num_n_blocks;
   int a_mode;                    // 0 tiled, 1 im2col, 2 halo
@@ -203,7 +214,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;   // num_m_blocks counts 128*CG-row tiles
+  const int num_tiles = p.num_tiles;               // tiles_per_batch (num_m_blocks counts 128*CG-row tiles) x batches
 
   // The producer and MMA warps keep their control flow WARP-UNIFORM (all 32 lanes walk the loops and wait on the
   // barriers) and elect one lane only around the TMA / tcgen05 instructions themselves: tile indices, stage
@@ -221,8 +232,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
       uint32_t aphase = 0;
       int tr_a = 0;
       for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
-        const int m_blk = (tile % p.num_m_blocks) * CG + (int)cta_rank;
+        const int tb = tile % p.tiles_per_batch;
+        const int m_blk = (tb % p.num_m_blocks) * CG + (int)cta_rank;
         const int m0 = m_blk * BM;
+        const int a_koff = ((tile / p.tiles_per_batch) % p.splits) * p.kchunk;      // 0 unless batched split-K
         int img = 0, ph = 0, qw = 0;
         if (p.a_mode == 1) {
           img = m0 / p.PQ;
@@ -252,7 +265,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
             if (p.debug_skip_mma & 2) mbar_arrive(a_full_bar);
             else {
             mbar_expect_tx(a_full_bar, p.a_tx_bytes);
-            if (p.a_mode == 0) tma_load_2d(dst, amap, a_full_bar, ac * BK, m0);
+            if (p.a_mode == 0) tma_load_2d(dst, amap, a_full_bar, ac * BK + a_koff, m0);
             else if (p.a_mode == 1) tma_load_im2col_4d(dst, amap, a_full_bar, cb * BK, qw, ph, img, (uint16_t)sx, (uint16_t)r);
             else tma_load_4d(dst, amap, a_full_bar, ac * BK, -1, ph, img);
             }
@@ -291,9 +304,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
         }
       } else {
       for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
-        const int n_blk = tile / p.num_m_blocks;
+        const int n_blk = (tile % p.tiles_per_batch) / p.num_m_blocks;
+        int b_koff = 0, b_row0 = 0;
+        if (p.splits > 1 || p.shift_w != 0) {
+          const int batch = tile / p.tiles_per_batch;
+          const int tap = batch / p.splits;
+          b_koff = (batch - tap * p.splits) * p.kchunk;
+          // TMA needs 16-byte aligned global addresses, so only the ROW part of a tap's shift (shift_w, a multiple
+          // of 8 elements) is applied as a coordinate; the column part selects one of three pre-shifted copies of the
+          // operand stacked along its row axis (vince_transpose_pad, copies = 3)
+          if (p.shift_w != 0) b_koff += (tap / 3 - 1) * p.shift_w, b_row0 = (tap % 3) * p.N;
+        }
         // this CTA's share of the weight tile (all of it, or its half when paired)
-        const int nrow = n_blk * BN + (int)cta_rank * (BN / CG);
+        const int nrow = b_row0 + n_blk * BN + (int)cta_rank * (BN / CG);
         for (int ac = 0; ac < p.a_chunks; ++ac) {
           for (int bi = 0; bi < p.b_per_a; ++bi) {
             mbar_wait(&b_empty[bs], bphase ^ 1);
@@ -306,7 +329,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
               if (p.debug_skip_mma & 4) mbar_arrive(&b_full[bs]);
               else {
                 mbar_expect_tx(&b_full[bs], B_TILE);
-                tma_load_2d(dst, bmap, &b_full[bs], kb * BK, nrow);
+                tma_load_2d(dst, bmap, &b_full[bs], kb * BK + b_koff, nrow);
               }
             }
             __syncwarp();
@@ -459,7 +482,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
     // kernel parameters used per chunk, read once (the asm barriers would otherwise force constant-bank re-reads)
     const bool has_stats = (EPI == 0) && p.stats != nullptr;
     const bool do_store = p.stats_only == 0;
-    const float alpha = p.alpha;
+    const float alpha = p.alpha * (p.alpha_dev != nullptr ? __ldg(p.alpha_dev) : 1.f);
     const int N = p.N;
     const long long M = p.M;
     const int relu = p.relu;
@@ -486,8 +509,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
     }
     // first global row and number of valid staging rows of a tile
     auto tile_rows = [&](int tile, long long& m0, int& nvalid, int& n_blk) {
-      const int m_blk = (tile % p.num_m_blocks) * CG + (int)cta_rank;
-      n_blk = tile / p.num_m_blocks;
+      const int tb = tile % p.tiles_per_batch;
+      const int m_blk = (tb % p.num_m_blocks) * CG + (int)cta_rank;
+      n_blk = tb / p.num_m_blocks;
       if (HALO) {
         const int img = m_blk / p.tiles_per_img;
         const int y0 = (m_blk - img * p.tiles_per_img) * p.TH;
@@ -540,7 +564,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
       long long m0;
       int nvalid, n_blk;
       tile_rows(tile, m0, nvalid, n_blk);
-      const int m_blk = (tile % p.num_m_blocks) * CG + (int)cta_rank;
+      const int m_blk = ((tile % p.tiles_per_batch) % p.num_m_blocks) * CG + (int)cta_rank;
+      const int out_row0 = (tile / p.tiles_per_batch) * p.out_batch_rows + m_blk * BM;
       int img = 0, y0 = 0;                         // halo mode: TMA store coordinates of the tile
       if (HALO) {
         img = m_blk / p.tiles_per_img;
@@ -702,8 +727,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
               tma_store_4d(&p.out_hi, src, c0, 0, y0, img);
               if (planes == 2) tma_store_4d(&p.out_lo, reinterpret_cast<const uint8_t*>(src) + 8192, c0, 0, y0, img);
             } else {
-              tma_store_2d(&p.out_hi, src, c0, m_blk * BM);
-              if (planes == 2) tma_store_2d(&p.out_lo, reinterpret_cast<const uint8_t*>(src) + 8192, c0, m_blk * BM);
+              tma_store_2d(&p.out_hi, src, c0, out_row0);
+              if (planes == 2) tma_store_2d(&p.out_lo, reinterpret_cast<const uint8_t*>(src) + 8192, c0, out_row0);
             }
             tma_store_commit();
           }
@@ -747,7 +772,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
           if (store_leader) {
             const void* src = staging + (buf - staging_s);
             if (HALO) tma_store_4d(&p.out, src, c0, 0, y0, img);
-            else tma_store_2d(&p.out, src, c0, m_blk * BM);
+            else tma_store_2d(&p.out, src, c0, out_row0);
             tma_store_commit();
           }
           store_pending = true;
@@ -830,6 +855,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
             const float sc = p.bn_gamma[c] * inv;
             p.bn_coef[c] = sc;
             p.bn_coef[N + c] = p.bn_beta[c] - (float)mean * sc;
+            if (p.bn_save) {                        // saved for the BatchNorm backward
+              p.bn_coef[2 * N + c] = (float)mean;
+              p.bn_coef[3 * N + c] = inv;
+            }
           }
           if (etid == 0 && p.bn_nbt != nullptr) *p.bn_nbt += 1;
         }
@@ -994,7 +1023,14 @@ static int halo_tile_rows(const ConvGemmDesc& d) {
 
 int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   VB_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "conv_gemm: empty problem M=%d N=%d K=%d", d.M, d.N, d.K);
-  VB_REQUIRE(d.K % BK == 0, "conv_gemm: K=%d must be a multiple of %d", d.K, BK);
+  const bool batched = d.kchunk > 0;               // batched split-K GEMM (weight gradients)
+  VB_REQUIRE(batched || d.K % BK == 0, "conv_gemm: K=%d must be a multiple of %d", d.K, BK);
+  if (batched) {
+    VB_REQUIRE(!d.im2col && !d.stats && !d.out_hi && !d.scale && !d.bias && d.out, "conv_gemm: batched split-K is a plain GEMM");
+    VB_REQUIRE(d.kchunk % BK == 0 && (d.taps == 1 || d.taps == 9), "conv_gemm: bad split-K geometry");
+    VB_REQUIRE(d.taps == 1 || (d.shift_w > 0 && d.shift_w % 8 == 0), "conv_gemm: shift_w must be a positive multiple of 8");
+    VB_REQUIRE(d.K % 8 == 0, "conv_gemm: split-K needs a 16-byte aligned row pitch (K %% 8 == 0)");
+  }
   VB_REQUIRE(d.N % 32 == 0, "conv_gemm: N=%d must be a multiple of 32", d.N);
   VB_REQUIRE(d.passes == 1 || d.passes == 3, "conv_gemm: passes must be 1 or 3");
   const bool planes_out = d.out_hi != nullptr;
@@ -1016,6 +1052,7 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   const size_t planes = d.passes == 3 ? 2 : 1;
   // CTA pairs (cta_group::2): worthwhile whenever there are at least a few 256-row tiles per SM pair
   int cg = ((d.M + BM - 1) / BM >= 8) ? 2 : 1;
+  if (batched) cg = 1;
   // at most 4 k-blocks per tile: the layer is bound by its epilogue / output stream, where the pair's cross-CTA
   // hand-shakes only cost (stem: 430 -> 399 us measured)
   if (d.K <= 4 * BK && !(getenv("VINCE_B200_SMALLK_PAIR") && atoi(getenv("VINCE_B200_SMALLK_PAIR")) == 1)) cg = 1;
@@ -1052,8 +1089,19 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   kp.debug_skip_mma = getenv("VINCE_B200_DEBUG_SKIP_MMA") ? atoi(getenv("VINCE_B200_DEBUG_SKIP_MMA")) : 0;
   kp.a_plane_bytes = BM * 128;
   kp.a_tx_bytes = BM * 128;
-  kp.a_chunks = d.K / BK;
+  kp.a_chunks = batched ? d.kchunk / BK : d.K / BK;
   kp.b_per_a = 1;
+  kp.splits = 1, kp.kchunk = 0, kp.shift_w = 0, kp.out_batch_rows = 0;
+  kp.alpha_dev = d.alpha_dev;
+  kp.bn_save = d.bn_save;
+  int nbatch = 1;
+  if (batched) {
+    kp.splits = (d.K + d.kchunk - 1) / d.kchunk;
+    kp.kchunk = d.kchunk;
+    kp.shift_w = d.taps == 9 ? d.shift_w : 0;
+    kp.out_batch_rows = ((d.M + BM - 1) / BM) * BM;
+    nbatch = d.taps * kp.splits;
+  }
   int rc;
   const int th = halo_tile_rows(d);
   if (d.im2col) {
@@ -1116,11 +1164,12 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
     }
   }
   // each CTA of a pair loads its half of the weight tile
-  rc = encode_tma_2d(&kp.b_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.b_hi, d.K, d.N, (uint64_t)d.K * 2, BK, bn / cg,
+  const uint64_t b_rows = (uint64_t)d.N * ((batched && d.taps == 9) ? 3 : 1);
+  rc = encode_tma_2d(&kp.b_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.b_hi, d.K, b_rows, (uint64_t)d.K * 2, BK, bn / cg,
                      CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   if (d.passes == 3) {
-    rc = encode_tma_2d(&kp.b_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.b_lo, d.K, d.N, (uint64_t)d.K * 2, BK, bn / cg,
+    rc = encode_tma_2d(&kp.b_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d.b_lo, d.K, b_rows, (uint64_t)d.K * 2, BK, bn / cg,
                        CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
@@ -1151,7 +1200,8 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
         if (rc) return rc;
       }
     } else if (d.out) {
-      rc = encode_tma_2d(&kp.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.out, d.N, d.M, (uint64_t)d.N * 4, 32, BM,
+      const uint64_t out_rows = batched ? (uint64_t)nbatch * kp.out_batch_rows : (uint64_t)d.M;
+      rc = encode_tma_2d(&kp.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.out, d.N, out_rows, (uint64_t)d.N * 4, 32, BM,
                          CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }
@@ -1167,11 +1217,11 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   // works through several tiles (otherwise the ring version overlaps the weight load just as well)
   const int total_kb = kp.a_chunks * kp.b_per_a;
   const bool res_ok = kp.num_n_blocks == 1 && (size_t)total_kb * b_stage + 2 * a_stage <= avail;
-  bool res = res_ok && (kp.num_m_blocks + cg - 1) / cg >= 2 * (num_sms() / cg);
+  bool res = !batched && res_ok && (kp.num_m_blocks + cg - 1) / cg >= 2 * (num_sms() / cg);
   {
     const char* e = getenv("VINCE_B200_RESIDENT");     // debug / A-B comparison: 0 disables, 2 forces when feasible
     if (e && atoi(e) == 0) res = false;
-    if (e && atoi(e) == 2) res = res_ok;
+    if (e && atoi(e) == 2) res = res_ok && !batched;
   }
   if (res) {
     kp.b_stages = total_kb;
@@ -1191,7 +1241,9 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   const size_t smem = fixed_smem(bn, d) + kp.a_stages * a_stage + kp.b_stages * b_stage;
   // 128-row blocks -> (128*cg)-row tiles; a pair whose second half lies past the end loads zeros and stores nothing
   kp.num_m_blocks = (kp.num_m_blocks + cg - 1) / cg;
-  const int tiles = kp.num_m_blocks * kp.num_n_blocks;
+  kp.tiles_per_batch = kp.num_m_blocks * kp.num_n_blocks;
+  kp.num_tiles = kp.tiles_per_batch * nbatch;
+  const int tiles = kp.num_tiles;
   int grid = tiles * cg < num_sms() ? tiles * cg : num_sms();
   if (getenv("VINCE_B200_DEBUG_GRID") && atoi(getenv("VINCE_B200_DEBUG_GRID")) < grid) grid = atoi(getenv("VINCE_B200_DEBUG_GRID"));
   const bool halo = kp.a_mode == 2;

@@ -221,9 +221,26 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const WeightPrepEntry*
                                                           __half* __restrict__ hi, __half* __restrict__ lo) {
   extern __shared__ float wbuf[];
   const WeightPrepEntry e = table[blockIdx.y];
+  const int RS = e.R * e.S;
+  if (e.kind == 2) {
+    // data-gradient weights: row ci of [Cin][R][S][Cout], k = (r', s', co) <- W[co][ci][R-1-r'][S-1-s'] (the flipped,
+    // channel-transposed filter: dX = conv_stride1(dilate(dY), W'))
+    const int ci = blockIdx.x;
+    if (ci >= e.Cin) return;
+    const int K = RS * e.Cout;
+    const int64_t dst = e.dst_off + (int64_t)ci * K;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      const int rs = k / e.Cout, co = k - rs * e.Cout;
+      const float w = __ldg(e.src + ((int64_t)co * e.Cin + ci) * RS + (RS - 1 - rs));
+      __half h, l;
+      split_f16(ldexpf(w, e.scale_log2), h, l);
+      hi[dst + k] = h;
+      if (lo) lo[dst + k] = l;
+    }
+    return;
+  }
   const int co = blockIdx.x;
   if (co >= e.Cout) return;
-  const int RS = e.R * e.S;
   const int K = e.kind == 1 ? 256 : RS * e.Cin;
   const int n_src = e.kind == 1 ? 147 : RS * e.Cin;
   const float* src = e.src + (int64_t)co * n_src;

@@ -50,6 +50,14 @@ struct ConvGemmDesc {
   const float* res_coef;
   // ---- statistics-only pass (needs stats): BatchNorm sums (+ finalize) are produced, nothing is stored
   int stats_only;
+  int bn_save;                // fused finalize also stores mean / inv-std: bn_coef is then [4][N]
+  const float* alpha_dev;     // optional device scalar multiplied into alpha
+  // ---- batched split-K GEMM (kchunk > 0; weight gradients): out[(tap*splits + split)*Mpad + m, n] =
+  //      sum_{k in split} A[m, k] * B[n, k + shift(tap)], K = full contraction extent, Mpad = M rounded up to 128,
+  //      shift(tap) = (tap/3 - 1)*shift_w + tap%3 - 1 for taps == 9, else 0; out-of-range k reads as zero
+  int kchunk;                 // K elements per split (multiple of 64)
+  int taps;                   // 1 or 9
+  int shift_w;
 };
 int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream);
 // eval-mode BatchNorm: coef[2][C] = (gamma / sqrt(running_var + eps), beta - running_mean * scale)
@@ -147,6 +155,55 @@ int infonce_bwd_launch(const InfoNceDesc& d, float grad_dist, int symmetric, int
 int masked_ce_launch(const float* sims, const uint8_t* mask, int R, int C, int nP, float temperature, float* dists,
                      float* weights, float* pos_sim, float* neg_max, float* row_lse, float* scalars, int* error_flag,
                      cudaStream_t stream);
+
+// ---- backward.cu (query-encoder backward) ------------------------------------------------
+// One conv+BN(+residual)(+ReLU) unit: dZ = (dA + dB) masked by the unit's ReLU; per-channel sums -> d gamma / d beta;
+// dRaw = gamma*invstd*(dZ - mean(dZ) - xhat*mean(dZ*xhat)) written as 2^e-scaled fp16 planes (optionally zero-dilated)
+// and / or fp32.  `work` = (3C + 2) doubles of scratch; afterwards work + 3C holds the floats (2^e, 2^-e).
+struct BnBwdDesc {
+  const float* dA;
+  const float* dB;
+  int bcast_hw;
+  int mask_kind;            // 0 none, 1 recompute relu(raw*scale + shift) > 0, 2 saved output planes > 0
+  const void* out_hi;
+  const void* out_lo;
+  const float* raw;
+  const float* coef;        // [4][C] scale, shift, mean, invstd (vince_conv_fwd with bn_save)
+  int64_t M;
+  int C;
+  double* work;
+  float* dgamma;            // optional [C]
+  float* dbeta;
+  int accumulate;           // add to dgamma / dbeta instead of overwriting
+  void* d_hi;               // optional planes of 2^e * dRaw
+  void* d_lo;
+  float* d_f32;             // optional fp32 dRaw
+  float* dz_out;            // optional masked dZ [M, C]
+  int dil, P, Q, Hd, Wd;
+};
+int bn_bwd_launch(const BnBwdDesc& d, cudaStream_t stream);
+int transpose_pad_launch(const __half* s_hi, const __half* s_lo, __half* d_hi, __half* d_lo, int64_t M, int C, int P,
+                         int Q, int st, int off, int Hp, int Wp, int64_t ld, int copies, cudaStream_t stream);
+int wgrad_reduce_launch(const float* part, int taps, int splits, int Mpad, int Cout, int Cin, const float* scale_dev,
+                        float scale, float* grad, int accumulate, cudaStream_t stream);
+int maxpool_bwd_launch(const float* dA, const float* dB, const float* raw, const float* coef, float* dst, int N, int P,
+                       int Q, int C, cudaStream_t stream);
+int stem_wgrad_launch(const float* x, const uint8_t* x8, const int64_t* gather_idx, const float* mean3,
+                      const float* std3, const float* draw, float* grad, int N, int H, int W, int accumulate,
+                      cudaStream_t stream);
+int sgemm_launch(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int ta, int tb,
+                 int accumulate, const float* relu_mask_src, cudaStream_t stream);
+int colsum_launch(const float* x, float* out, int R, int C, int accumulate, cudaStream_t stream);
+int normalize_bwd_launch(const float* x, const float* dy, float* dx, int rows, int D, float eps, float gscale,
+                         cudaStream_t stream);
+struct SgdChunk {
+  float* param;
+  const float* grad;
+  float* buf;               // momentum buffer (null: no momentum)
+  int64_t count;
+};
+int sgd_launch(const SgdChunk* table_dev, int n_chunks, float lr, float momentum, float weight_decay, float grad_scale,
+               int first_step, cudaStream_t stream);
 
 // ---- knn.cu ------------------------------------------------------------------------------------------------
 // exact k-NN of every row of feats [n, D] among all rows (Euclidean), self match dropped; nbr_idx [n, k],

@@ -105,10 +105,11 @@ class _Arena:
     """Static activation allocator used while a plan is being built: a freed buffer is handed to the next request it
     fits (best fit).  Safe because the plan always replays in the same order on one stream."""
 
-    def __init__(self, device):
+    def __init__(self, device, keep=False):
         self.device = device
         self.free_list = []         # (nbytes, tensor)
         self.total = 0
+        self.keep = keep            # taping mode: nothing is recycled (the backward reads every activation)
 
     def alloc(self, shape, dtype):
         numel = 1
@@ -130,6 +131,8 @@ class _Arena:
         return t
 
     def free(self, *tensors):
+        if self.keep:
+            return
         for t in tensors:
             if t is not None and hasattr(t, "_arena_raw"):
                 self.free_list.append(t._arena_raw)
@@ -145,7 +148,7 @@ class Act:
 
 class _Plan:
     __slots__ = ("launches", "stats", "idx_gather", "idx_scatter", "x_hi", "x_lo", "final", "out_shape", "arena_bytes",
-                 "n_static")
+                 "n_static", "tape", "shape", "last_input", "last_gather")
 
 
 class EncoderRunner:
@@ -169,16 +172,19 @@ class EncoderRunner:
                     entry["down"] = ConvSpec(blk.downsample[0].weight, blk.downsample[1], blk.stride, 0)
                 specs += entry["convs"] + ([entry["down"]] if entry["down"] is not None else [])
                 self.blocks.append(entry)
-        # per conv, in one fp64 work buffer: [2*Cout] batch sums | [Cout] = 2*Cout fp32 (scale, shift) | [1] counter
+        # per conv, in one fp64 work buffer: [2*Cout] batch sums | [2*Cout] = 4*Cout fp32 (scale, shift, and - when a
+        # backward will follow - batch mean, inv-std) | [1] counter
         off = 0
         for s in specs:
             s.stats_off = off
-            off += 3 * s.Cout + 2        # (+1 pad: keeps every region 16-byte aligned for float4 coefficient loads)
+            off += 4 * s.Cout + 2        # (+1 pad: keeps every region 16-byte aligned for float4 coefficient loads)
         self.stats_total = off
         self.bank = WeightBank(specs, passes)
         self.launches = 0          # kernels launched by the last forward (bench bookkeeping)
         self.input_mean, self.input_std = ops.IMAGENET_MEAN, ops.IMAGENET_STD     # used for uint8 HWC inputs only
         self._plans = {}
+        self._taping = False        # building / running a plan that keeps everything the backward needs
+        self.tape = None            # the plan of the last taped forward (read by vince_b200.backward.EncoderBackward)
         self.block_n_override = None
         import os
         self.halo_mode = int(os.environ.get("VINCE_B200_HALO", "-1"))   # -1 auto, 0 off, 1 force (3x3 stride-1 convs)
@@ -213,8 +219,8 @@ class EncoderRunner:
         o, C = spec.stats_off, spec.Cout
         if not train:
             return {}
-        return dict(stats=work[o:o + 2 * C], bn=spec.bn, coef=work[o + 2 * C:o + 3 * C].view(torch.float32),
-                    counter=work[o + 3 * C:o + 3 * C + 1].view(torch.int32))
+        return dict(stats=work[o:o + 2 * C], bn=spec.bn, coef=work[o + 2 * C:o + 4 * C].view(torch.float32),
+                    counter=work[o + 4 * C:o + 4 * C + 1].view(torch.int32), bn_save=self._taping)
 
     def _conv_geom(self, act, spec):
         P = (act.H + 2 * spec.pad - spec.R) // spec.stride + 1
@@ -226,8 +232,9 @@ class EncoderRunner:
         return P, Q, act.N * P * Q, geom
 
     def _coef(self, spec, work):
+        """[4*Cout] fp32: scale | shift | batch mean | inv-std (the last two only in taping mode)"""
         o, C = spec.stats_off, spec.Cout
-        return work[o + 2 * C:o + 3 * C].view(torch.float32)
+        return work[o + 2 * C:o + 4 * C].view(torch.float32)
 
     def _build_conv(self, arena, act, spec, work, train, launches):
         """raw fp32 conv output (+ train-mode BatchNorm sums / finalize into the plan's work buffer)"""
@@ -238,6 +245,7 @@ class EncoderRunner:
                                            geom=geom, block_n=self._block_n(M, spec.Cout), halo_mode=self.halo_mode,
                                            alpha=WEIGHT_ALPHA,
                                            **self._bn_args(spec, work, train)))
+        self._last_unit = dict(spec=spec, x=act, raw=raw, coef=self._coef(spec, work), P=P, Q=Q, M=M, out=None)
         return raw, P, Q
 
     def _two_pass(self, spec):
@@ -271,7 +279,9 @@ class EncoderRunner:
                 kw["res_bn"] = ops.bn_side(*res_side)
             launches.append(ops.build_bn_apply(self._side(raw, spec, work), M, C, relu, hi, lo, **kw))
             arena.free(raw)
-            return Act(hi, lo, act.N, P, Q, C), P, Q
+            out = Act(hi, lo, act.N, P, Q, C)
+            self._last_unit["out"] = out
+            return out, P, Q
         if train:
             launches.append(ops.build_conv_fwd(act.hi, act.lo, w_hi, w_lo, None, M, C, spec.K, stats_only=True,
                                                **common, **self._bn_args(spec, work, train)))
@@ -293,10 +303,14 @@ class EncoderRunner:
     def _side(self, raw, spec, work):
         return ops.bn_side(raw, self._coef(spec, work))
 
-    def _build_plan(self, N, H, W, train, dev):
+    def _build_plan(self, N, H, W, train, dev, tape=False):
+        """tape=True (train mode, a backward will follow): no activation buffer is recycled, the convolutions also
+        store the batch mean / inv-std, and plan.tape records, per conv+BN unit, what the backward needs."""
         plan = _Plan()
-        arena = _Arena(dev)
+        self._taping = bool(tape)
+        arena = _Arena(dev, keep=tape)
         launches = []
+        tape_blocks = []
         # BN work buffer (sums, coefficients, finalize counters); zeroed once per train-mode forward
         stats = work = torch.zeros((self.stats_total,), device=dev, dtype=torch.float64)
         plan.stats = work
@@ -317,6 +331,7 @@ class EncoderRunner:
         launches.append(ops.build_conv_fwd(plan.x_hi, plan.x_lo, w_hi, w_lo, raw, M, 64, 256, passes=self.passes,
                                            geom=dict(sg["geom"], batch=N), alpha=WEIGHT_ALPHA,
                                            **self._bn_args(self.stem, work, train)))
+        tape_stem = dict(spec=self.stem, raw=raw, coef=self._coef(self.stem, work), N=N, H=H, W=W, P=P, Q=Q)
         arena.free(plan.x_hi, plan.x_lo)
         P2, Q2 = (P - 1) // 2 + 1, (Q - 1) // 2 + 1
         hi, lo = self._planes(arena, N * P2 * Q2, 64)
@@ -328,8 +343,11 @@ class EncoderRunner:
             last = bi == len(self.blocks) - 1
             cur = act
             convs = blk["convs"]
+            tb = dict(input=act, units=[], down=None, out=None, last=last)
+            tape_blocks.append(tb)
             for spec in convs[:-1]:
                 nxt, p_, q_ = self._build_conv_planes(arena, cur, spec, work, train, launches, relu=True)
+                tb["units"].append(self._last_unit)
                 if cur is not act:
                     arena.free(cur.hi, cur.lo)
                 cur = nxt
@@ -338,12 +356,14 @@ class EncoderRunner:
             if last:
                 # last block: raw outputs feed the fused relu(bn+residual) -> NCHW + global-average-pool kernel
                 raw, p_, q_ = self._build_conv(arena, cur, spec, work, train, launches)
+                tb["units"].append(self._last_unit)
                 if cur is not act:
                     arena.free(cur.hi, cur.lo)
                 kw = {}
                 raw_ds = None
                 if down is not None:
                     raw_ds, _, _ = self._build_conv(arena, act, down, work, train, launches)
+                    tb["down"] = self._last_unit
                     kw["res_bn"] = self._side(raw_ds, down, stats)
                 else:
                     kw["res_planes"] = (act.hi, act.lo)
@@ -358,8 +378,11 @@ class EncoderRunner:
                 # downsample branch: raw fp32 output; its BatchNorm is applied where the residual is added (the apply
                 # epilogue of the main convolution, or vince_bn_apply) - same bytes as identity planes, exact fp32 add
                 raw_ds, _, _ = self._build_conv(arena, act, down, work, train, launches)
+                tb["down"] = self._last_unit
                 res = dict(res_side=(raw_ds, self._coef(down, work)))
             nxt, p_, q_ = self._build_conv_planes(arena, cur, spec, work, train, launches, relu=True, **res)
+            tb["units"].append(self._last_unit)
+            tb["out"] = nxt
             if cur is not act:
                 arena.free(cur.hi, cur.lo)
             arena.free(raw_ds, act.hi, act.lo)
@@ -367,10 +390,13 @@ class EncoderRunner:
         plan.launches = launches
         plan.arena_bytes = arena.total
         plan.n_static = len(launches)
+        plan.tape = dict(stem=tape_stem, blocks=tape_blocks, pool_out=tape_blocks[0]["input"]) if tape else None
+        plan.shape = (N, H, W)
+        self._taping = False
         return plan
 
     # ------------------------------------------------------------------------------------------
-    def forward(self, x, train, gather_idx=None, scatter_idx=None, want_spatial=True, patch_grid=1):
+    def forward(self, x, train, gather_idx=None, scatter_idx=None, want_spatial=True, patch_grid=1, tape=False):
         """x: [N,3,H,W] fp32 CUDA (the reference's normalised frames), or [N,H,W,3] uint8 CUDA (raw HWC frames: the
         ToTensor(scale=255) + Normalize(self.input_mean, self.input_std) of utils/transforms.py:89-101 is then fused
         into the stem packing).  patch_grid=3 runs the trunk over the 9N jigsaw patches of the N frames
@@ -399,14 +425,20 @@ class EncoderRunner:
                 raise ValueError("the jigsaw patch path keeps frames in place (no gather / scatter index)")
         with torch.cuda.device(dev):
             self.bank.refresh()
-            key = (N, H, W, bool(train), self.two_pass, self.fold_eval, dev.index, self.bank.generation)
+            tape = bool(tape and train)
+            two_pass = 0 if tape else self.two_pass        # the backward reads the raw tensors: no recompute route
+            key = (N, H, W, bool(train), two_pass, self.fold_eval, tape, dev.index, self.bank.generation)
             if self._plans and next(iter(self._plans))[-1] != self.bank.generation:
                 self._plans.clear()                         # parameters moved: every cached pointer is stale
             plan = self._plans.get(key)
             if plan is None:
                 if len(self._plans) >= 4:                   # bound the number of resident activation arenas
                     self._plans.pop(next(iter(self._plans)))
-                plan = self._build_plan(N, H, W, bool(train), dev)
+                saved_tp, self.two_pass = self.two_pass, two_pass
+                try:
+                    plan = self._build_plan(N, H, W, bool(train), dev, tape=tape)
+                finally:
+                    self.two_pass = saved_tp
                 self._plans[key] = plan
             if train:
                 plan.stats.zero_()
@@ -428,6 +460,9 @@ class EncoderRunner:
             pooled = torch.empty((N, f["C"]), device=dev, dtype=torch.float32)
             ops.build_bn_final_pool(f["main"], f["N"], f["HW"], f["C"], spatial, pooled, scatter_idx=si, **f["kw"])()
             self.launches = plan.n_static + 3 + (1 if train else 0)       # + weight_prep, stem_pack, final (+ memset)
+            if tape:
+                plan.last_input, plan.last_gather = x, gi
+                self.tape = plan
         return spatial, pooled
 
 

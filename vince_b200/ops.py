@@ -71,7 +71,8 @@ def build_bn_eval_coef(bn, coef):
 # ---------------------------------------------------------------------------------------------------------------
 def build_conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, block_n=0, scale=None, bias=None,
                    relu=False, stats=None, bn=None, coef=None, counter=None, halo_mode=-1, alpha=1.0,
-                   out_planes=None, ep_coef=None, res_planes=None, res_raw=None, res_coef=None, stats_only=False):
+                   out_planes=None, ep_coef=None, res_planes=None, res_raw=None, res_coef=None, stats_only=False,
+                   bn_save=False, alpha_dev=None, kchunk=0, taps=1, shift_w=0):
     """geom=None: A is [M,K]; else dict(batch,H,W,Cin,R,S,stride,pad_lo_h,pad_lo_w,pad_hi_h,pad_hi_w) (NHWC gather).
     bn/coef/counter (with stats): fuse the train-mode BatchNorm finalize of module `bn` into the kernel tail.
     stats_only: statistics pass (nothing stored; `out` may be None).
@@ -83,7 +84,7 @@ def build_conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, bl
     d.w_hi = _val(w_hi, torch.float16, "w_hi")
     d.w_lo = _val(w_lo, torch.float16, "w_lo")
     d.out = _val(out, torch.float32, "out")
-    if out is not None and out.numel() < M * N:
+    if out is not None and kchunk == 0 and out.numel() < M * N:
         raise ValueError("conv_fwd: output buffer too small")
     if out is None and out_planes is None and not stats_only:
         raise ValueError("conv_fwd: no output")
@@ -103,6 +104,9 @@ def build_conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, bl
     d.halo_mode = halo_mode
     d.alpha = float(alpha)
     d.stats_only = 1 if stats_only else 0
+    d.bn_save = 1 if bn_save else 0
+    d.alpha_dev = _val(alpha_dev, torch.float32, "alpha_dev")
+    d.kchunk, d.taps, d.shift_w = int(kchunk), int(taps), int(shift_w)
     if out_planes is not None:
         if out is not None or ep_coef is None:
             raise ValueError("conv_fwd: the apply epilogue writes planes only and needs ep_coef")
@@ -151,7 +155,7 @@ def build_conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, bl
         else:
             check(fn(ref, stream), "vince_conv_fwd")
     run._keep = (d, a_hi, a_lo, w_hi, w_lo, out, scale, bias, stats, bn, coef, counter, out_planes, ep_coef, res_planes,
-                 res_raw, res_coef)
+                 res_raw, res_coef, alpha_dev)
     return run
 
 

@@ -328,10 +328,11 @@ class VinceModel(BaseModel):
             num_total += batch_size
         return mini_batch_list
 
-    def extract_features(self, inputs, run_average_layer=True, gather_idx=None, scatter_idx=None, patch_grid=1):
+    def extract_features(self, inputs, run_average_layer=True, gather_idx=None, scatter_idx=None, patch_grid=1,
+                         tape=False):
         return_val = {}
         spatial, pooled = self.feature_extractor(inputs, gather_idx=gather_idx, scatter_idx=scatter_idx,
-                                                 want_pooled=True, patch_grid=patch_grid)
+                                                 want_pooled=True, patch_grid=patch_grid, tape=tape)
         self.launches += self.feature_extractor.module.runner.launches
         return_val["spatial_features"] = spatial
         if run_average_layer:
@@ -365,6 +366,11 @@ class VinceModel(BaseModel):
         cross = getattr(self, "cross_shuffle", None) if shuffle else None
         if cross is not None:
             return self._get_embeddings_cross_shuffled(inputs, jigsaw, jigsaw_orders, cross)
+        # A backward may follow (vince_solver.py:463-469) when gradients are enabled on a training-mode model with
+        # trainable parameters: the encoder then keeps a tape (no buffer recycling, saved BatchNorm statistics)
+        taping = (torch.is_grad_enabled() and self.training and not jigsaw
+                  and any(p.requires_grad for p in self.embedding.parameters()))
+        self._train_tape = None
         with torch.no_grad():
             data = inputs["data"]
             n = data.shape[0]
@@ -379,11 +385,15 @@ class VinceModel(BaseModel):
                     return_val = self._jigsaw_embeddings(data, shuffle_order, jigsaw_orders)
                 else:
                     # shuffle gather folded into the stem's loads, un-shuffle into the last block's stores
-                    return_val = self.extract_features(data, gather_idx=shuffle_order, scatter_idx=shuffle_order)
+                    return_val = self.extract_features(data, gather_idx=shuffle_order, scatter_idx=shuffle_order,
+                                                       tape=taping)
                     head = self._heads["embedding"]
                     head.refresh()
                     hidden = head.linear(0, return_val["extracted_features"], relu=True)
                     output = head.linear(1, hidden, relu=False)
+                    if taping:
+                        self._train_tape = dict(pooled=return_val["extracted_features"], hidden=hidden, prenorm=output,
+                                                shuffle_order=shuffle_order)
                     self.launches += head.launches
                     return_val["prenorm_features"] = output
                     emb = torch.empty_like(output)
@@ -558,17 +568,42 @@ class VinceModel(BaseModel):
             self.__dict__["_anchor"] = a
         return a
 
-    def _backward(self, network_outputs, loss_name, grad_out):
-        """Called by autograd when the solver runs loss.backward().  The query-encoder backward (conv dgrad / wgrad,
-        BatchNorm backward, projection head) is SURVEY.md 8f rank 1 and is not built: fail loudly and say what
-        exists instead of silently leaving every .grad empty."""
-        raise NotImplementedError(
-            "vince_b200: loss.backward() reached the fused InfoNCE loss (%s), but the query-encoder backward is not "
-            "implemented (SURVEY.md 8f rank 1): this build scores (forward, loss, metrics, EMA, enqueue) and provides "
-            "d loss / d embeddings through VinceModel.embedding_gradients(network_outputs); it cannot train. "
-            "Wrap the scoring step in torch.no_grad() to use the loss value only." % loss_name)
+    supports_backward = True
 
-    def embedding_gradients(self, network_outputs: Dict, loss_weights: Optional[Dict[str, float]] = None):
+    def _backward(self, network_outputs, loss_name, grad_out):
+        """Called by autograd when the solver runs loss.backward() (vince_solver.py:463-469): d loss / d embeddings with
+        the fused InfoNCE backward kernel, then the projection head and the ResNet trunk from the tape of the last
+        training-mode forward (vince_b200/backward.py).  Gradients are accumulated into `param.grad`."""
+        from .backward import EncoderBackward, GradSlots, HeadBackward
+        tape = getattr(self, "_train_tape", None)
+        if tape is None:
+            raise NotImplementedError(
+                "vince_b200: loss.backward() needs the tape of a training-mode get_embeddings() call made with gradients "
+                "enabled on this model (the jigsaw branch and the cross-GPU shuffle have no backward yet: SURVEY.md 8f)")
+        key = "main" if loss_name == "nce_loss" else "self"
+        weight = float(grad_out)
+        with torch.no_grad():
+            dq = self.embedding_gradients(network_outputs, {loss_name: weight}, only=key)
+            dev = dq.device
+            slots = self.__dict__.get("_grad_slots")
+            if slots is None:
+                slots = self.__dict__["_grad_slots"] = GradSlots(list(self.parameters()))
+            slots.begin(dev)
+            d_pooled = HeadBackward.run([self.embedding[0], self.embedding[2]], tape, dq.contiguous(), slots)
+            if tape["shuffle_order"] is not None:
+                d_pooled = d_pooled.index_select(0, tape["shuffle_order"])     # internal row i = frame shuffle_order[i]
+            runner = self.feature_extractor.module.runner
+            eb = self.__dict__.get("_encoder_backward")
+            if eb is None or eb.runner is not runner:
+                eb = self.__dict__["_encoder_backward"] = EncoderBackward(runner)
+            eb.run(d_pooled, slots)
+            slots.end()
+            self.backward_launches = eb.launches + 12
+            sync = getattr(self, "grad_sync", None)
+            if sync is not None:
+                sync(slots)
+
+    def embedding_gradients(self, network_outputs: Dict, loss_weights: Optional[Dict[str, float]] = None, only=None):
         """d(sum of weighted losses)/d(embeddings) [B, D] with the fused backward kernel: the tensor autograd hands to
         the projection head when vince_solver.py:465 calls loss.backward() (keys / queue are detached,
         vince_model.py:598,610).  `loss_weights` maps "nce_loss" / "nce_loss_self" to their weights (default 1.0, as
@@ -578,7 +613,7 @@ class VinceModel(BaseModel):
         dq = None
         with torch.no_grad(), torch.cuda.device(network_outputs["embeddings"].device):
             for key, lname in (("main", "nce_loss"), ("self", "nce_loss_self")):
-                if key not in fused:
+                if key not in fused or (only is not None and key != only):
                     continue
                 q, keys, queue_tf32, nf, T = fused[key]["_operands"]
                 dq = ops.infonce_bwd(q, keys, queue_tf32, nf, T, fused[key], grad_dist=loss_weights.get(lname, 1.0),
