@@ -343,6 +343,17 @@ def run_ours(a):
         return ms
 
     data, queue_data = hp.devbuf[kind]
+    if a.profile_train:              # under ncu: capture exactly one full training step
+        for _ in range(3):
+            hp.step(data, queue_data, train=True)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        hp.step(data, queue_data, train=True)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        if rank == 0:
+            emit({"profile_train": True, "config": wl["cfg"]})
+        return
     warm = max(a.warmup, 3)
     for _ in range(warm):
         hp.step(data, queue_data)
@@ -699,6 +710,7 @@ def main():
                     help="uint8 = raw HWC frames, normalisation fused into the stem packing (default: the format the "
                          "reference's workers hold); fp32 = the reference's normalised NCHW tensors")
     ap.add_argument("--no-train", action="store_true", help="skip the extra full-training-step leg")
+    ap.add_argument("--profile-train", action="store_true", help="one full training step between profiler start/stop (ncu)")
     ap.add_argument("--profile-only", action="store_true",
                     help="stop after the device-resident timed steps (for runs under ncu; prints no bench value)")
     a = ap.parse_args()

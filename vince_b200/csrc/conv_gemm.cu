@@ -980,7 +980,8 @@ static int auto_block_n(const ConvGemmDesc& d, int cg) {
       const size_t stage = ((size_t)BM * 128 + (size_t)(bn / cg) * 128) * planes;
       if (bn > 64 && fixed_smem(bn, d) + 2 * stage > SMEM_BUDGET) continue;
     }
-    const long tiles = m_blocks * ((d.N + bn - 1) / bn);
+    long tiles = m_blocks * ((d.N + bn - 1) / bn);
+    if (d.kchunk > 0) tiles *= (long)d.taps * ((d.K + d.kchunk - 1) / d.kchunk);     // batched split-K: every batch
     const long waves = (tiles + units - 1) / units;
     const long passes = d.passes == 3 ? 3 : 1;
     // per MMA: the tensor pipe needs bn/2 cycles, the issuing thread ~50 (measured with the 32-bit-descriptor issue
@@ -1054,8 +1055,11 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   int cg = ((d.M + BM - 1) / BM >= 8) ? 2 : 1;
   if (batched) cg = 1;
   // at most 4 k-blocks per tile: the layer is bound by its epilogue / output stream, where the pair's cross-CTA
-  // hand-shakes only cost (stem: 430 -> 399 us measured)
-  if (d.K <= 4 * BK && !(getenv("VINCE_B200_SMALLK_PAIR") && atoi(getenv("VINCE_B200_SMALLK_PAIR")) == 1)) cg = 1;
+  // hand-shakes only cost (stem: 430 -> 399 us measured with single CTAs); with at least 128 output channels and two k-blocks the pair's
+  // halved weight traffic wins again (ResNet-50 256->1024: 114 -> 99 us, 128->512: 158 -> 144 us, r02 conv_variants)
+  if (d.K <= 4 * BK && (d.N <= 64 || d.K <= BK) &&
+      !(getenv("VINCE_B200_SMALLK_PAIR") && atoi(getenv("VINCE_B200_SMALLK_PAIR")) == 1))
+    cg = 1;
   {
     const char* e = getenv("VINCE_B200_CTA_PAIR");     // 0 forces single-CTA tiles (debug / A-B comparison)
     if (e && atoi(e) == 0) cg = 1;
