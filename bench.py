@@ -490,6 +490,7 @@ def run_ours(a):
     cpu = cpu_baseline(wl, seconds=20.0) if world == 1 else {
         "value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "reference",
         "sample": "not measured at N>1 (see the N=1 line of the same run, or --impl reference)"}
+    ref_gpu = reference_same_gpu(wl, dev) if (world == 1 and not a.no_ref_gpu) else None
     wire = {"uint8": "uint8 HWC raw frames (the dataset workers' format), ToTensor+Normalize fused into the stem packing",
             "fp32": "fp32 NCHW normalised frames (the reference's post-transform wire format)"}
     line = {
@@ -511,6 +512,7 @@ def run_ours(a):
         "infonce_step_what": "similarity+CE+metrics + %sEMA + enqueue, device resident, B=%d K=%d D=%d" % (
             "key all-gather + " if world > 1 else "", wl["B"], wl["K"], wl["D"]),
         "train_step": train,
+        "reference_same_gpu": ref_gpu,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "ms_per_step": round(e2e_ms / e2e_steps, 4),
                 "h2d_bytes_per_step": h2d_main, "d2h_bytes_per_step": 4, "steps": e2e_steps,
@@ -605,6 +607,73 @@ def reference_step_runner(wl, B):
         ph.add("whole_step", time.perf_counter() - t0)
         return float(out["losses"]["nce_loss"])
     return step, ph, "port"
+
+
+def reference_same_gpu(wl, dev, steps=5):
+    """For context (not the contract's reference arm): the UNMODIFIED reference (oracle/_ref: PyTorch eager + cuDNN,
+    torch's default math modes - TF32 allowed for convolutions, fp32 matmuls) running the same forward-only step on this
+    very GPU, full batch, CUDA-event timed.  Answers "what would the reference's own GPU path do on a B200"."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import ref_loader
+        if not ref_loader.reference_available():
+            return None
+        import warnings
+        warnings.simplefilter("ignore")
+        ref = ref_loader.load_reference()
+        B = wl["B"]
+        args = ref_loader.make_args(backbone=wl["backbone"], num_frames=wl["nf"], batch_size=B, queue_size=wl["K"],
+                                    embedding_size=wl["D"], temperature=wl["T"], momentum=wl["m"], jigsaw=wl["jigsaw"])
+        args.feature_extractor_gpu_ids = [dev]
+        args.pytorch_gpu_ids = [dev]
+        torch.manual_seed(0)
+        model = ref.VinceModel(args)
+        model.to(dev)
+        model.train()
+        qm = ref.VinceQueueModel(args, model)
+        qm.to(dev)
+        qm.train()
+        queue = ref.StorageQueue(wl["K"], wl["D"], device=dev)
+        g = torch.Generator().manual_seed(1234)
+        data = torch.randn((B, 3, wl["H"], wl["H"]), generator=g).to(dev)
+        queue_data = torch.randn((B, 3, wl["H"], wl["H"]), generator=g).to(dev)
+        coin = random.Random(2020)
+
+        def step():
+            batch = {"data": data, "queue_data": queue_data, "batch_types": ["images"], "batch_sizes": [B],
+                     "data_source": "synthetic", "num_frames": wl["nf"]}
+            with torch.no_grad():
+                kj = wl["jigsaw"] and coin.random() < 0.5
+                queue_batches = qm(batch, jigsaw=kj, shuffle=True)
+                outputs = model.get_embeddings(batch, jigsaw=wl["jigsaw"] and not kj, shuffle=True)
+                output = outputs[0]
+                output.update(queue.dequeue())
+                output.update({"data_source": "synthetic", "num_frames": wl["nf"]})
+                output.update(queue_batches[0])
+                output.update(model(output))
+                model.loss(output)
+                model.get_metrics(output)
+                queue.enqueue(output["queue_embeddings"], [None] * B, "synthetic")
+                qm.vince_update(model)
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        del model, qm, queue
+        torch.cuda.empty_cache()
+        return {"value": round(2 * B / (ms / 1e3), 1), "unit": "frames/s", "ms_per_step": round(ms, 3), "steps": steps,
+                "what": "the unmodified reference (oracle/_ref; PyTorch %s eager + cuDNN, default math modes: TF32 "
+                        "convolutions allowed) running the same forward-only step on this GPU at batch=%d - context "
+                        "only; the contract's reference arm is the CPU run" % (torch.__version__, B)}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:200]}
 
 
 def cpu_sample_batch(wl):
@@ -710,6 +779,7 @@ def main():
                     help="uint8 = raw HWC frames, normalisation fused into the stem packing (default: the format the "
                          "reference's workers hold); fp32 = the reference's normalised NCHW tensors")
     ap.add_argument("--no-train", action="store_true", help="skip the extra full-training-step leg")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the extra reference-on-this-GPU context leg")
     ap.add_argument("--profile-train", action="store_true", help="one full training step between profiler start/stop (ncu)")
     ap.add_argument("--profile-only", action="store_true",
                     help="stop after the device-resident timed steps (for runs under ncu; prints no bench value)")

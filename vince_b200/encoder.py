@@ -184,6 +184,7 @@ class EncoderRunner:
         self.input_mean, self.input_std = ops.IMAGENET_MEAN, ops.IMAGENET_STD     # used for uint8 HWC inputs only
         self._plans = {}
         self._taping = False        # building / running a plan that keeps everything the backward needs
+        self._last_unit = None      # the conv + BN unit most recently added to the plan under construction
         self.tape = None            # the plan of the last taped forward (read by vince_b200.backward.EncoderBackward)
         self.block_n_override = None
         import os
@@ -293,7 +294,10 @@ class EncoderRunner:
             kw["res_raw"], kw["res_coef"] = res_side
         launches.append(ops.build_conv_fwd(act.hi, act.lo, w_hi, w_lo, None, M, C, spec.K, relu=relu,
                                            out_planes=(hi, lo), ep_coef=self._coef(spec, work), **common, **kw))
-        return Act(hi, lo, act.N, P, Q, C), P, Q
+        out = Act(hi, lo, act.N, P, Q, C)
+        # (no raw tensor on this route: such plans are never taped - forward() disables the two-pass route when taping)
+        self._last_unit = dict(spec=spec, x=act, raw=None, coef=self._coef(spec, work), P=P, Q=Q, M=M, out=out)
+        return out, P, Q
 
     def _planes(self, arena, M, C):
         hi = arena.alloc((M, C), torch.float16)
