@@ -83,7 +83,10 @@ typedef struct {
   int32_t stats_only;     /* 1: statistics pass - `stats` (+ the fused finalize) are produced, nothing is stored
                            * (`out` may be NULL).  First half of the train-mode two-pass scheme for wide 1x1 convolutions:
                            * pass 1 computes the batch statistics, pass 2 recomputes the GEMM with the apply epilogue,
-                           * so the raw [M,N] fp32 tensor and the separate vince_bn_apply pass never touch HBM */
+                           * so the raw [M,N] fp32 tensor and the separate vince_bn_apply pass never touch HBM.
+                           * 2 (ABI v4; im2col == 0 only): the same pass with the operand roles swapped inside the kernel
+                           * (accumulator rows = output channels, columns = pixels), which turns the per-channel sums
+                           * into in-register adds: 2.8x faster on the 56x56 64->256 expansion (74 vs 207 us) */
   /* "apply" epilogue (ABI v2), selected by out_hi != NULL (then out must be NULL and stats / scale / bias unused):
    *   planes(out) = relu?( alpha*acc*ep_coef[c] + ep_coef[N+c] + residual )
    * replaces: nn.BatchNorm2d (eval mode, or train mode with coefficients from a statistics pass) + the residual add
@@ -190,7 +193,10 @@ int vince_jigsaw_gather(const float* in, const int64_t* order, float* out, int32
 
 /* ---- fused InfoNCE forward ----------------------------------------------------------------------------------
  * replaces: VinceModel.forward similarity matmuls (vince_model.py:213-233), loss_util.similarity_cross_entropy
- *           (utils/loss_util.py:7-62) and the metric passes of VinceModel.get_metrics (vince_model.py:314-342). */
+ *           (utils/loss_util.py:7-62) and the metric passes of VinceModel.get_metrics (vince_model.py:314-342).
+ * ONE kernel launch (ABI v4): q / keys are exact fp32 (16-byte aligned, D a multiple of 32, <= 128) and are rounded to
+ * TF32 inside the kernel; the last CTA of each 128-row query block merges the per-CTA (max, sum-exp) partials, adds the
+ * exact-fp32 positives and writes the per-row outputs, the last CTA overall reduces the five scalars. */
 typedef struct {
   const float* q;
   const float* keys;

@@ -48,6 +48,8 @@ def main():
     ap.add_argument("--passes", type=int, default=3)
     ap.add_argument("--nostats", action="store_true")
     ap.add_argument("--statsonly", action="store_true")
+    ap.add_argument("--tstats", action="store_true", help="transposed statistics pass (1x1 stride-1 shapes only)")
+    ap.add_argument("--apply", type=int, default=-1, help="apply epilogue: 0 no residual, 1 residual planes, 2 bn(raw) residual")
     a = ap.parse_args()
     dev = "cuda"
     B = a.batch
@@ -69,14 +71,33 @@ def main():
         if not (R == 1 and stride == 1):
             geom = dict(batch=B, H=H, W=W, Cin=Cin, R=R, S=R, stride=stride, pad_lo_h=pad, pad_lo_w=pad, pad_hi_h=pad, pad_hi_w=pad)
         runs = []
+        if a.tstats and geom is not None:
+            continue
+        coef = torch.cat([torch.rand(Cout, device=dev) + 0.5, torch.randn(Cout, device=dev)])
+        planes = [(torch.empty((M, Cout), device=dev, dtype=torch.float16), torch.empty((M, Cout), device=dev, dtype=torch.float16))
+                  for _ in range(nbuf)] if a.apply >= 0 else None
+        res_p = (torch.randn((M, Cout), device=dev).to(torch.float16), (torch.randn((M, Cout), device=dev) * 0.01).to(torch.float16)) \
+            if a.apply == 1 else None
+        res_r = torch.randn((M, Cout), device=dev) if a.apply == 2 else None
         for i in range(nbuf):
             hi, lo = acts[i]
             x_hi = hi.reshape(-1, Cin) if geom is None else hi
             x_lo = lo.reshape(-1, Cin) if geom is None else lo
+            if a.apply >= 0:
+                kw = {}
+                if a.apply == 1:
+                    kw["res_planes"] = res_p
+                elif a.apply == 2:
+                    kw["res_raw"], kw["res_coef"] = res_r, coef
+                runs.append(ops.build_conv_fwd(x_hi, x_lo, w_hi, w_lo, None, M, Cout, K, passes=a.passes, geom=geom,
+                                               block_n=a.bn, halo_mode=a.halo, relu=True, out_planes=planes[i],
+                                               ep_coef=coef, **kw))
+                continue
+            so = 2 if a.tstats else (1 if a.statsonly else 0)
             runs.append(ops.build_conv_fwd(x_hi, x_lo if a.passes == 3 else None, w_hi, w_lo if a.passes == 3 else None,
-                                           None if a.statsonly else outs[i], M, Cout, K, passes=a.passes, geom=geom,
+                                           None if so else outs[i], M, Cout, K, passes=a.passes, geom=geom,
                                            block_n=a.bn, stats=None if a.nostats else stats, halo_mode=a.halo,
-                                           stats_only=a.statsonly))
+                                           stats_only=so))
         for r in runs:
             r()
         torch.cuda.synchronize()

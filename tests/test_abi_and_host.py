@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(dll, n), "missing export: " + n
     assert set(names) == set(_lib.SIGNATURES), (set(names) ^ set(_lib.SIGNATURES))
-    assert dll.vince_abi_version() == 3
+    assert dll.vince_abi_version() == 4
     assert int(dll.vince_infonce_workspace_bytes(256, 128)) > 2 * 256 * 128 * 4
 
 

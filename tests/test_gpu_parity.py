@@ -460,16 +460,17 @@ def test_fused_epilogue_routes_equal_separate_bn_apply_bitwise(backbone, B, H):
     x = torch.randn((B, 3, H, H), generator=gen).to(DEV)
     snap = {k: v.clone() for k, v in model.state_dict().items()}
     res = {}
-    import time
-    for mode, train in (("separate", True), ("fused", True), ("separate", False), ("fused", False)):
+    saved = (runner.two_pass, runner.fold_eval, runner.tstats)
+    for mode, train in (("separate", True), ("fused", True), ("fused_t", True), ("separate", False), ("fused", False)):
         model.load_state_dict(snap)
         model.train(train)
-        runner.two_pass = runner.fold_eval = 1 if mode == "fused" else 0
+        runner.two_pass = runner.fold_eval = 0 if mode == "separate" else 1
+        runner.tstats = 1 if mode == "fused_t" else 0
         out = model.get_embeddings({"data": x})
         torch.cuda.synchronize()
         res[(mode, train)] = (out["embeddings"].clone(), out["spatial_features"].clone(),
                               {k: v.clone() for k, v in model.state_dict().items() if "running" in k})
-    runner.two_pass = runner.fold_eval = 1
+    runner.two_pass, runner.fold_eval, runner.tstats = saved
     for train in (True, False):
         a, b = res[("separate", train)], res[("fused", train)]
         assert torch.equal(a[0], b[0]), "embeddings differ (train=%s)" % train
@@ -477,6 +478,51 @@ def test_fused_epilogue_routes_equal_separate_bn_apply_bitwise(backbone, B, H):
         for k in a[2]:
             assert torch.equal(a[2][k], b[2][k]), k
     assert not torch.equal(res[("fused", True)][0], res[("fused", False)][0])
+    # transposed statistics pass: the same sums accumulated in another order (per channel over 256-pixel tiles, then
+    # fp64) - equal to rounding of the fp32 coefficients, not bit for bit
+    a, b = res[("separate", True)], res[("fused_t", True)]
+    e_emb, e_sp = rel(b[0], a[0]), rel(b[1], a[1])
+    e_run = max(rel(b[2][k], a[2][k]) for k in a[2] if not k.endswith("num_batches_tracked"))
+    print("%s B=%d %d^2 transposed-statistics route vs separate bn_apply: embeddings %.2e spatial %.2e running stats %.2e"
+          % (backbone, B, H, e_emb, e_sp, e_run))
+    assert e_emb < 2e-6 and e_sp < 2e-6 and e_run < 1e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(802816, 256, 64), (6272, 512, 128), (98, 64, 64), (1000, 384, 192), (50176, 1024, 256)])
+def test_transposed_statistics_pass_matches_fp64_sums(M, N, K):
+    """vince_conv_fwd stats_only=2 (channels on the accumulator rows, in-register sums) against fp64 column sums of
+    the same fp16x3 product and against the untransposed statistics pass; ragged M (TMA zero fill), N < 128, N not a
+    multiple of 256 (single-CTA tiles) and the benchmark's largest shape."""
+    from vince_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn((M, K), generator=gen).to(DEV).relu_()
+    w = (torch.randn((N, K), generator=gen) * 0.1).to(DEV)
+    x_hi, x_lo = x.half(), (x - x.half().float()).half()
+    w_hi, w_lo = w.half(), (w - w.half().float()).half()
+    sums = {}
+    for so in (1, 2):
+        stats = torch.zeros((2 * N,), device=DEV, dtype=torch.float64)
+        ops.conv_fwd(x_hi, x_lo, w_hi, w_lo, None, M, N, K, stats=stats, stats_only=so, alpha=0.5)
+        torch.cuda.synchronize()
+        sums[so] = stats
+    xe, we = x_hi.double() + x_lo.double(), w_hi.double() + w_lo.double()
+    ref_s, ref_q = torch.zeros(N, device=DEV, dtype=torch.float64), torch.zeros(N, device=DEV, dtype=torch.float64)
+    for r0 in range(0, M, 65536):
+        y = 0.5 * (xe[r0:r0 + 65536] @ we.t())
+        ref_s += y.sum(0)
+        ref_q += (y * y).sum(0)
+    ref = torch.cat([ref_s, ref_q])
+    # natural scale of each sum: |sum y| <= sqrt(M * sum y^2); the accumulators both passes read carry the tensor core's
+    # own fp32 rounding (a few 1e-8 of the output rms per element, not zero-mean), so against fp64 the bar is 2e-4 of that
+    # scale, while the two passes - which consume identical accumulators - must agree to fp32 summation accuracy
+    scale = ref.abs() + 1e-3 * (ref_q * M).sqrt().repeat(2) + 1e-30
+    for so in (1, 2):
+        err = ((sums[so] - ref).abs() / scale).max().item()
+        print("stats_only=%d M=%d N=%d K=%d: max rel err of the sums vs fp64 %.2e" % (so, M, N, K, err))
+        assert err < 2e-4, (so, err)
+    agree = ((sums[1] - sums[2]).abs() / scale).max().item()
+    print("transposed vs untransposed statistics pass: %.2e" % agree)
+    assert agree < 2e-6
 
 
 def test_cfg4_resnet50_jigsaw_full_size_vs_oracle():

@@ -294,8 +294,7 @@ class EncoderBackward:
             cached = self._replay.get(id(plan))
             if cached is not None and cached["sig"] == sig:
                 cached["d_in"].copy_(d_pooled)
-                for fn in cached["launches"]:
-                    fn()
+                cached["graph"]()                           # the recorded launch list, as one CUDA graph launch
                 self._stem_wgrad(plan, cached["draw"], cached["stem_grad"], cached["stem_acc"])
                 for p in cached["params"]:
                     slots.written.add(id(p))
@@ -310,7 +309,7 @@ class EncoderBackward:
             finally:
                 rec, self._rec = self._rec, None
             params = [p for p in slots.params if id(p) in slots.written and id(p) not in written_before]
-            self._replay = {id(plan): dict(sig=sig, launches=rec, d_in=d_in, draw=draw, stem_grad=stem_grad,
+            self._replay = {id(plan): dict(sig=sig, launches=rec, graph=ops.GraphReplay(rec), d_in=d_in, draw=draw, stem_grad=stem_grad,
                                            stem_acc=stem_acc, params=params, n=self.launches, plan=plan)}
 
     def _stem_wgrad(self, plan, draw, grad, acc):

@@ -30,7 +30,7 @@ static int check_side(const vince_bn_side* s, const char* what) {
 extern "C" {
 
 const char* vince_last_error(void) { return get_error(); }
-int vince_abi_version(void) { return 3; }
+int vince_abi_version(void) { return 4; }
 
 int vince_conv_fwd(const vince_conv_desc* d, void* stream) {
   VB_REQUIRE(d != nullptr, "vince_conv_fwd: null descriptor");

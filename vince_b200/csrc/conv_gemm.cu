@@ -41,6 +41,10 @@ constexpr size_t SMEM_BUDGET = 226 * 1024;    // of 227 KB: leaves the 1 KB syst
 struct GemmKernelParams {
   CUtensorMap a_hi, a_lo, b_hi, b_lo, out;
   CUtensorMap out_hi, out_lo;    // EPI == 1: fp16 (hi, lo) output planes (box 32 channels x 128 rows, SWIZZLE_64B)
+  CUtensorMap res_a, res_b;      // EPI == 1 residual tiles, same boxes as the output: (hi, lo) planes (res_kind 1) or
+                                 // res_a = the raw fp32 tensor (res_kind 2; box 32 x 128 fp32, SWIZZLE_128B)
+  int res_bufs;                  // residual tiles in flight (TMA ring depth, <= 4)
+  uint32_t res_tx_bytes;         // bytes one residual tile delivers (both planes)
   int staging_bufs;              // output staging tiles in shared memory (1 or 2)
   uint32_t staging_total;        // bytes of the staging area: staging_bufs output tiles (+ 2 residual tiles, EPI == 1)
   // EPI == 1 ("apply" epilogue): out = relu?( acc*alpha*coef[c] + coef[N+c] + residual ) split into fp16 planes
@@ -51,6 +55,7 @@ struct GemmKernelParams {
   const float* res_raw;
   const float* res_coef;
   int stats_only;                // EPI == 0: accumulate BatchNorm sums / finalize but store nothing
+  int stat_channels;             // BatchNorm channels: N, or (EPI == 2, transposed statistics pass) the kernel's M extent
   // batched split-K GEMM (weight gradients; tiled A mode only): tile -> (batch, m_blk, n_blk), batch -> (tap, split);
   // A k-offset = split * kchunk; B k-offset = split * kchunk + (tap/3 - 1) * shift_w and B rows (tap%3) * N + n for
   // taps == 9 (B = three column-shifted copies stacked along the rows); output rows batch * out_batch_rows + m
@@ -134,6 +139,10 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 // scale/shift (BatchNorm with known coefficients) + residual + ReLU, written as the fp16 (hi, lo) planes the next
 // convolution consumes: eval-mode BatchNorm folded into the producing convolution (resnet.py:76-92,117-137), and the
 // second pass of the train-mode "statistics pass + recompute pass" scheme for wide 1x1 convolutions.
+// EPI = 2: TRANSPOSED statistics pass, the first pass of that scheme: the launcher swaps the operand roles (kernel rows =
+// output channels from the weight matrix, kernel columns = pixels), so an accumulator ROW holds one channel over BN
+// pixels and a thread's tcgen05.ld delivers 32 values of ITS channel - BatchNorm sum / sum of squares are then plain
+// in-register adds (no staging tile, no barrier, no cross-thread reduction) and nothing is stored at all.
 template <int BN, int CG, bool HALO, bool RES, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -160,7 +169,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
   uint64_t* b_empty = b_full + MAX_RING;
   uint64_t* tmem_full = b_empty + MAX_RING;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_full = tmem_empty + 2;             // [4] residual tile ring (EPI == 1)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 4);
   uint32_t* last_flag = tmem_ptr + 1;
   double* smem_stats = reinterpret_cast<double*>(tmem_ptr + 2);     // [4 epilogue warps][2][BN], warp-private
 
@@ -170,7 +180,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
     if (EPI == 1) {
       tma_prefetch_desc(&p.out_hi);
       tma_prefetch_desc(&p.out_lo);
-    } else {
+      if (p.res_kind != 0) tma_prefetch_desc(&p.res_a);
+      if (p.res_kind == 1 && p.res_lo != nullptr) tma_prefetch_desc(&p.res_b);
+    } else if (EPI == 0) {
       tma_prefetch_desc(&p.out);
     }
     if (planes == 2) {
@@ -194,6 +206,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], CG == 2 ? 8 : 128);    // pair: one arrive per epilogue warp of both CTAs
     }
+    for (int s = 0; s < 4; ++s) mbar_init(&res_full[s], 1);
     fence_mbar_init();
   }
   if (warp == 4) {
@@ -205,7 +218,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
       tmem_relinquish();
     }
   }
-  if (threadIdx.x >= EPI_TID0) {
+  if (EPI == 0 && threadIdx.x >= EPI_TID0) {       // (EPI 1 keeps 4 x BN coefficients there, EPI 2 nothing)
     for (int i = threadIdx.x - EPI_TID0; i < 8 * BN + 2; i += 128) smem_stats[i] = 0.0;
   }
   tc_fence_before_sync();
@@ -480,7 +493,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
     const uint32_t staging_s = smem_u32(staging);
     const int nbuf = p.staging_bufs;               // 1 or 2 output staging tiles
     // kernel parameters used per chunk, read once (the asm barriers would otherwise force constant-bank re-reads)
-    const bool has_stats = (EPI == 0) && p.stats != nullptr;
+    const bool has_stats = (EPI != 1) && p.stats != nullptr;
     const bool do_store = p.stats_only == 0;
     const float alpha = p.alpha * (p.alpha_dev != nullptr ? __ldg(p.alpha_dev) : 1.f);
     const int N = p.N;
@@ -492,7 +505,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
     const float* const ep_scale = p.scale;
     const float* const ep_bias = p.bias;
     const uint32_t stats_s = smem_u32(smem_stats + 1);        // 16-byte aligned: [4 warps][BN] x {sum, err, sq, err}
-    const uint32_t res_s = staging_s + (uint32_t)nbuf * STAGING_BYTES;      // EPI == 1: two residual tiles
+    const uint32_t res_s = staging_s + (uint32_t)nbuf * STAGING_BYTES;      // EPI == 1: the residual tile ring
     // halo mode: which output pixel (if any) this accumulator row is
     int hy = 0, hx = 0;
     if (HALO) {
@@ -523,42 +536,88 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
       }
       if (m0 + nvalid > M) nvalid = (int)(M - m0 > 0 ? M - m0 : 0);
     };
-    // EPI == 1: asynchronous, coalesced prefetch (cp.async, 16 bytes per request) of the residual tile of (tile,
-    // chunk) into residual buffer `rbuf`, laid out with the same XOR swizzles as the output staging tiles so that the
-    // row-owner reads below are bank-conflict free
-    auto prefetch_residual = [&](int tile, int chunk, uint32_t rbuf) {
-      if (res_kind != 0 && tile < num_tiles) {
-        long long m0;
-        int nvalid, n_blk;
-        tile_rows(tile, m0, nvalid, n_blk);
-        const int c0 = n_blk * BN + chunk * 32;
-        const uint32_t dst = res_s + rbuf * STAGING_BYTES;
-        if (res_kind == 1) {
-          const int piece = etid & 3, r0 = etid >> 2;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int sr = r0 + 32 * j;
-            if (sr < nvalid) {
-              const uint32_t off = (uint32_t)(sr * 64 + ((piece ^ ((sr >> 1) & 3)) << 4));
-              const long long g = (m0 + sr) * N + c0 + piece * 8;
-              cp_async_16(dst + off, p.res_hi + g);
-              if (p.res_lo != nullptr) cp_async_16(dst + 8192u + off, p.res_lo + g);
+    // EPI == 1: the residual tile of every chunk is fetched by TMA (one elected thread, same box and swizzle as the
+    // output tile, so the row-owner reads below are bank-conflict free) into a ring of `res_bufs` tiles: with a single
+    // tile in flight per SM the residual stream was latency-bound (16 KB x 148 SMs in flight ~ 1.6 TB/s); chunk k of this
+    // CTA (counted across tiles) uses tile k % res_bufs and phase (k / res_bufs) & 1 of its barrier.
+    constexpr int CHUNKS = BN / 32;
+    const int rbufs = p.res_bufs;
+    auto issue_residual = [&](uint32_t k) {
+      const int tile = tile_start + (int)(k / CHUNKS) * tile_step;
+      if (tile >= num_tiles) return;
+      const int chunk = (int)(k % CHUNKS);
+      const int tb = tile % p.tiles_per_batch;
+      const int m_blk = (tb % p.num_m_blocks) * CG + (int)cta_rank;
+      const int c0 = (tb / p.num_m_blocks) * BN + chunk * 32;
+      const uint32_t b = k % (uint32_t)rbufs;
+      uint8_t* dst = staging + (size_t)(nbuf + (int)b) * STAGING_BYTES;
+      mbar_expect_tx(&res_full[b], p.res_tx_bytes);
+      if (HALO) {
+        const int img = m_blk / p.tiles_per_img;
+        const int y0 = (m_blk - img * p.tiles_per_img) * p.TH;
+        tma_load_4d(dst, &p.res_a, &res_full[b], c0, 0, y0, img);
+        if (res_kind == 1 && p.res_lo != nullptr) tma_load_4d(dst + 8192, &p.res_b, &res_full[b], c0, 0, y0, img);
+      } else {
+        tma_load_2d(dst, &p.res_a, &res_full[b], c0, m_blk * BM);
+        if (res_kind == 1 && p.res_lo != nullptr) tma_load_2d(dst + 8192, &p.res_b, &res_full[b], c0, m_blk * BM);
+      }
+    };
+    if (EPI == 1 && res_kind != 0 && store_leader)
+      for (int k = 0; k < rbufs; ++k) issue_residual((uint32_t)k);
+    if (EPI == 2) {
+      // ---- transposed statistics pass: this thread owns channel (m_blk * 128 + row) of every tile it sees ----
+      const int NC = p.stat_channels;
+      float s_hi = 0.f, s_er = 0.f, q_hi = 0.f, q_er = 0.f;      // double-float (value, error) running sums
+      int cur_ch = -1;
+      auto flush = [&]() {
+        if (cur_ch >= 0 && cur_ch < NC && p.stats != nullptr) {
+          const double a = (double)alpha;
+          atomicAdd(&p.stats[cur_ch], ((double)s_hi + (double)s_er) * a);
+          atomicAdd(&p.stats[NC + cur_ch], ((double)q_hi + (double)q_er) * a * a);
+        }
+        s_hi = s_er = q_hi = q_er = 0.f;
+      };
+      for (int tile = tile_start; tile < num_tiles; tile += tile_step, ++local_t) {
+        const int acc = local_t & 1;
+        const uint32_t acc_phase = (local_t >> 1) & 1;
+        const int m_blk = ((tile % p.tiles_per_batch) % p.num_m_blocks) * CG + (int)cta_rank;
+        const int ch = m_blk * BM + row;
+        if (ch != cur_ch) {
+          flush();
+          cur_ch = ch;
+        }
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+          uint32_t raw[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk * 32, raw);
+          tmem_ld_wait();
+          if (chunk == BN / 32 - 1) {
+            tc_fence_before_sync();
+            if (CG == 2) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(tmem_empty_leader[acc]);
+            } else {
+              mbar_arrive(&tmem_empty[acc]);
             }
           }
-        } else {
-          const int piece = etid & 7, r0 = etid >> 3;
+          // pixels past the end of the activation matrix were zero-filled by TMA: they add nothing
+          float sa = 0.f, sb = 0.f, sc = 0.f, sd = 0.f, qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int sr = r0 + 16 * j;
-            if (sr < nvalid)
-              cp_async_16(dst + (uint32_t)(sr * 128 + ((piece ^ (sr & 7)) << 4)), p.res_raw + (m0 + sr) * N + c0 + piece * 4);
+          for (int i = 0; i < 32; i += 4) {
+            const float x0 = __uint_as_float(raw[i]), x1 = __uint_as_float(raw[i + 1]);
+            const float x2 = __uint_as_float(raw[i + 2]), x3 = __uint_as_float(raw[i + 3]);
+            sa += x0, sb += x1, sc += x2, sd += x3;
+            qa = fmaf(x0, x0, qa), qb = fmaf(x1, x1, qb), qc = fmaf(x2, x2, qc), qd = fmaf(x3, x3, qd);
           }
+          two_sum_acc(s_hi, s_er, (sa + sb) + (sc + sd));
+          two_sum_acc(q_hi, q_er, (qa + qb) + (qc + qd));
         }
       }
-      cp_async_commit();
-    };
-    if (EPI == 1) prefetch_residual(tile_start, 0, 0u);
-    for (int tile = tile_start; tile < num_tiles; tile += tile_step, ++local_t) {
+      flush();
+    }
+    for (int tile = (EPI == 2 ? num_tiles : tile_start); tile < num_tiles; tile += tile_step, ++local_t) {
       const int acc = local_t & 1;
       const uint32_t acc_phase = (local_t >> 1) & 1;
       long long m0;
@@ -640,17 +699,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
           }
         }
         if (EPI == 1) {
-          const uint32_t rcur = res_s + (chunk_ctr & 1u) * STAGING_BYTES;
-          // residual tile of THIS chunk has landed (mine: wait_group; everybody's: the barrier), and every thread is
-          // done with the output staging tile / the residual tile of two chunks ago
-          if (res_kind != 0) cp_async_wait_all();
-          if (nbuf == 1 && store_leader && store_pending) tma_store_wait_read0();
-          if (res_kind != 0 || nbuf == 1) named_bar_sync(2, 128);
-          {
-            // prefetch the next chunk's residual tile into the other buffer
-            int nt = tile, nc = chunk + 1;
-            if (nc == BN / 32) nt = tile + tile_step, nc = 0;
-            prefetch_residual(nt, nc, (chunk_ctr + 1u) & 1u);
+          const uint32_t rslot = chunk_ctr % (uint32_t)rbufs;
+          const uint32_t rcur = res_s + rslot * STAGING_BYTES;
+          // the residual tile of THIS chunk has landed (TMA, mbarrier); with one output staging tile everybody must
+          // also be done with the previous chunk's tile before it is overwritten
+          if (res_kind != 0) mbar_wait(&res_full[rslot], (chunk_ctr / (uint32_t)rbufs) & 1u);
+          if (nbuf == 1) {
+            if (store_leader && store_pending) tma_store_wait_read0();
+            named_bar_sync(2, 128);
           }
           const uint32_t cfs = stats_s + (uint32_t)(chunk * 32) * 4u;
           // two 8 KB tiles (hi | lo) of 64-byte rows; 16-byte piece j of row `srow` stored at j ^ ((srow >> 1) & 3),
@@ -731,6 +787,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
               if (planes == 2) tma_store_2d(&p.out_lo, reinterpret_cast<const uint8_t*>(src) + 8192, c0, out_row0);
             }
             tma_store_commit();
+            // every thread has passed the barrier, i.e. is done reading this chunk's residual tile: refill it
+            if (res_kind != 0) issue_residual(chunk_ctr + (uint32_t)rbufs);
           }
           store_pending = true;
           continue;
@@ -811,7 +869,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
         }
       }
     }
-    if (EPI == 1) cp_async_wait_all();
     if (store_leader) tma_store_wait0();
     if (has_stats) {
       if (cur_n_blk >= 0) {
@@ -842,6 +899,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
         named_bar_sync(1, 128);
         if (*last_flag) {
           __threadfence();
+          const int N = p.stat_channels;            // (shadows the kernel's column extent: they differ when EPI == 2)
           for (int c = etid; c < N; c += 128) {
             const double mean = __ldcg(&p.stats[c]) / p.bn_count;
             double var = __ldcg(&p.stats[N + c]) / p.bn_count - mean * mean;
@@ -925,11 +983,16 @@ static int staging_tiles(const ConvGemmDesc& d) {
   if (e && (atoi(e) == 1 || atoi(e) == 2)) nbuf = atoi(e);
   return nbuf;
 }
+// residual tiles of the apply epilogue (TMA ring): as many as fit next to a 2-stage operand ring, at most 4
 static size_t staging_bytes(const ConvGemmDesc& d) {
-  return (size_t)STAGING_BYTES * (staging_tiles(d) + ((d.out_hi != nullptr && d.res_kind != 0) ? 2 : 0));
+  if (d.stats_only == 2) return 0;                   // transposed statistics pass: nothing is staged
+  return (size_t)STAGING_BYTES * (staging_tiles(d) + ((d.out_hi != nullptr && d.res_kind != 0) ? (d.res_tiles > 0 ? d.res_tiles : 2) : 0));
 }
 static size_t fixed_smem(int bn, const ConvGemmDesc& d) {
-  return 1024 /*align slack*/ + staging_bytes(d) + (4 * MAX_RING + 4) * 8 + 32 + 8 * bn * 8;
+  // alignment slack + staging + barriers + flags + per-channel area (EPI 0: [4 warps][2][bn] double-float sums,
+  // EPI 1: 4 x bn coefficients, EPI 2: unused)
+  const size_t chan = d.out_hi != nullptr ? (size_t)4 * bn * 4 + 16 : (d.stats_only == 2 ? 16 : (size_t)8 * bn * 8);
+  return 1024 + staging_bytes(d) + (4 * MAX_RING + 8) * 8 + 32 + chan;
 }
 
 template <int BN, int CG, bool HALO, bool RES, int EPI>
@@ -1022,7 +1085,22 @@ static int halo_tile_rows(const ConvGemmDesc& d) {
   return th;
 }
 
-int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
+int conv_gemm_launch(const ConvGemmDesc& d_in, cudaStream_t stream) {
+  ConvGemmDesc d = d_in;
+  // Transposed statistics pass (stats_only == 2; 1x1 stride-1 convolutions / plain GEMMs only): the operand roles are
+  // swapped - kernel rows = the N output channels (weights as the A operand), kernel columns = the M pixels
+  // (activations as the B operand, 256 per tile) - so that every accumulator row is one channel (EPI = 2 above).
+  const bool tstats = d.stats_only == 2;
+  const int stat_channels = d.N;
+  const double stat_count = (double)d.M;
+  if (tstats) {
+    VB_REQUIRE(!d.im2col && d.kchunk == 0, "conv_gemm: the transposed statistics pass handles plain [M,K] x [N,K] GEMMs");
+    VB_REQUIRE(d.stats && !d.out && !d.out_hi && !d.scale && !d.bias && !d.relu,
+               "conv_gemm: the transposed statistics pass produces BatchNorm sums only");
+    d.a_hi = d_in.b_hi, d.a_lo = d_in.b_lo, d.b_hi = d_in.a_hi, d.b_lo = d_in.a_lo;
+    d.M = d_in.N, d.N = d_in.M;
+    d.block_n = 256;
+  }
   VB_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "conv_gemm: empty problem M=%d N=%d K=%d", d.M, d.N, d.K);
   const bool batched = d.kchunk > 0;               // batched split-K GEMM (weight gradients)
   VB_REQUIRE(batched || d.K % BK == 0, "conv_gemm: K=%d must be a multiple of %d", d.K, BK);
@@ -1032,7 +1110,7 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
     VB_REQUIRE(d.taps == 1 || (d.shift_w > 0 && d.shift_w % 8 == 0), "conv_gemm: shift_w must be a positive multiple of 8");
     VB_REQUIRE(d.K % 8 == 0, "conv_gemm: split-K needs a 16-byte aligned row pitch (K %% 8 == 0)");
   }
-  VB_REQUIRE(d.N % 32 == 0, "conv_gemm: N=%d must be a multiple of 32", d.N);
+  VB_REQUIRE(tstats || d.N % 32 == 0, "conv_gemm: N=%d must be a multiple of 32", d.N);
   VB_REQUIRE(d.passes == 1 || d.passes == 3, "conv_gemm: passes must be 1 or 3");
   const bool planes_out = d.out_hi != nullptr;
   VB_REQUIRE(d.a_hi && d.b_hi && (d.out || planes_out || d.stats_only), "conv_gemm: null operand");
@@ -1046,6 +1124,7 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
     VB_REQUIRE(d.res_kind != 2 || (d.res_raw && d.res_coef), "conv_gemm: residual raw / coefficients null");
   }
   VB_REQUIRE(!d.stats_only || d.stats, "conv_gemm: stats_only without a stats buffer");
+  VB_REQUIRE(d.stats_only >= 0 && d.stats_only <= 2, "conv_gemm: stats_only must be 0, 1 or 2");
   VB_REQUIRE(d.passes == 1 || (d.a_lo && d.b_lo), "conv_gemm: fp16x3 needs lo planes");
   VB_REQUIRE(!(d.stats && (d.bias || d.scale || d.relu)), "conv_gemm: stats are defined on raw accumulators only");
   VB_REQUIRE(!d.bn_coef || (d.stats && d.bn_gamma && d.bn_beta && d.bn_running_mean && d.bn_running_var && d.bn_counter),
@@ -1060,6 +1139,12 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   if (d.K <= 4 * BK && (d.N <= 64 || d.K <= BK) &&
       !(getenv("VINCE_B200_SMALLK_PAIR") && atoi(getenv("VINCE_B200_SMALLK_PAIR")) == 1))
     cg = 1;
+  if (tstats) {
+    // a pair covers 256 channels x 256 pixels per tile: each CTA loads its 128 weight rows and half of the pixel tile
+    cg = (d.M % 256 == 0) ? 2 : 1;
+    const char* e = getenv("VINCE_B200_TSTATS_PAIR");  // debug / A-B comparison: 0 single CTAs, 1 pairs when possible
+    if (e && atoi(e) == 0) cg = 1;
+  }
   {
     const char* e = getenv("VINCE_B200_CTA_PAIR");     // 0 forces single-CTA tiles (debug / A-B comparison)
     if (e && atoi(e) == 0) cg = 1;
@@ -1083,7 +1168,8 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   kp.bn_gamma = d.bn_gamma, kp.bn_beta = d.bn_beta, kp.bn_running_mean = d.bn_running_mean;
   kp.bn_running_var = d.bn_running_var, kp.bn_nbt = reinterpret_cast<long long*>(d.bn_num_batches_tracked);
   kp.bn_coef = d.bn_coef, kp.bn_counter = d.bn_counter, kp.bn_momentum = d.bn_momentum, kp.bn_eps = d.bn_eps;
-  kp.bn_count = (double)d.M;
+  kp.bn_count = stat_count;
+  kp.stat_channels = stat_channels;
   kp.trace = reinterpret_cast<unsigned long long*>(d.trace);
   kp.stats_only = d.stats_only;
   kp.ep_coef = d.ep_coef;
@@ -1210,12 +1296,39 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
       if (rc) return rc;
     }
   }
-  kp.staging_bufs = staging_tiles(d);
-  kp.staging_total = (uint32_t)staging_bytes(d);
-
   // ---- shared-memory budget: A ring + B ring ----
   const size_t a_stage = (size_t)kp.a_plane_bytes * planes;
   const size_t b_stage = (size_t)(bn / cg) * 128 * planes;
+  if (planes_out && d.res_kind != 0) {
+    // residual ring: as deep as fits next to a 2-stage operand ring (tile-width / halo decisions above assumed 2)
+    int want = 4;
+    const char* e = getenv("VINCE_B200_RES_TILES");    // debug / A-B comparison: 2..4
+    if (e && atoi(e) >= 2 && atoi(e) <= 4) want = atoi(e);
+    for (d.res_tiles = want; d.res_tiles > 2; --d.res_tiles)
+      if (fixed_smem(bn, d) + 2 * (a_stage + b_stage) <= SMEM_BUDGET) break;
+    kp.res_bufs = d.res_tiles;
+    // same boxes as the output tiles
+    const bool raw = d.res_kind == 2;
+    const CUtensorMapDataType dt = raw ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const CUtensorMapSwizzle sw = raw ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const void* ra = raw ? (const void*)d.res_raw : d.res_hi;
+    const bool two = !raw && d.res_lo != nullptr;
+    if (kp.a_mode == 2) {
+      rc = encode_tma_4d_nhwc(&kp.res_a, dt, ra, d.batch, d.H, d.W, d.N, 32, d.W, kp.TH, sw);
+      if (rc) return rc;
+      if (two) rc = encode_tma_4d_nhwc(&kp.res_b, dt, d.res_lo, d.batch, d.H, d.W, d.N, 32, d.W, kp.TH, sw);
+      if (rc) return rc;
+      kp.res_tx_bytes = (uint32_t)(32 * d.W * kp.TH) * (raw ? 4u : (two ? 4u : 2u));
+    } else {
+      rc = encode_tma_2d(&kp.res_a, dt, ra, d.N, d.M, (uint64_t)d.N * (raw ? 4 : 2), 32, BM, sw);
+      if (rc) return rc;
+      if (two) rc = encode_tma_2d(&kp.res_b, dt, d.res_lo, d.N, d.M, (uint64_t)d.N * 2, 32, BM, sw);
+      if (rc) return rc;
+      kp.res_tx_bytes = (uint32_t)(32 * BM) * (raw ? 4u : (two ? 4u : 2u));
+    }
+  }
+  kp.staging_bufs = staging_tiles(d);
+  kp.staging_total = (uint32_t)staging_bytes(d);
   const size_t avail = SMEM_BUDGET - fixed_smem(bn, d);
   // resident weights: single n-block, this CTA's whole weight share + two activation stages fit, and every CTA
   // works through several tiles (otherwise the ring version overlaps the weight load just as well)
@@ -1227,6 +1340,7 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
     if (e && atoi(e) == 0) res = false;
     if (e && atoi(e) == 2) res = res_ok && !batched;
   }
+  if (tstats) res = false;
   if (res) {
     kp.b_stages = total_kb;
     int st = (int)((avail - (size_t)total_kb * b_stage) / a_stage);
@@ -1252,6 +1366,10 @@ int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream) {
   if (getenv("VINCE_B200_DEBUG_GRID") && atoi(getenv("VINCE_B200_DEBUG_GRID")) < grid) grid = atoi(getenv("VINCE_B200_DEBUG_GRID"));
   const bool halo = kp.a_mode == 2;
   if (cg == 2) grid &= ~1;
+  if (tstats) {
+    return cg == 2 ? launch_gemm<256, 2, false, false, 2>(kp, smem, grid, stream)
+                   : launch_gemm<256, 1, false, false, 2>(kp, smem, grid, stream);
+  }
 #define VB_LAUNCH_E(BN_, CG_, EPI_)                                                             \
   {                                                                                             \
     if (halo) return res ? launch_gemm<BN_, CG_, true, true, EPI_>(kp, smem, grid, stream)      \

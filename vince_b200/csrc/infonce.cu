@@ -1,19 +1,22 @@
 // Fused InfoNCE forward for sm_100a (replaces vince_model.py:198-250 cat+mm, loss_util.py:7-62 and the
 // metric passes of vince_model.py:314-342): the [B, Bk+K] similarity matrix is never written.
 //
-//   main kernel   : persistent, warp-specialised.  Each CTA owns one 128-row block of queries (resident in
+//   ONE launch (B > 0 and at least one column tile):
+//   main loop     : persistent, warp-specialised.  Each CTA owns one 128-row block of queries (resident in
 //                   shared memory) and a contiguous range of 128-column tiles of [keys || queue]; tiles are
 //                   streamed by TMA, multiplied on the tensor cores (tcgen05 kind::tf32, fp32 accumulate in
 //                   double-buffered TMEM) and consumed straight from TMEM by 128 epilogue threads (one query
 //                   row each) that keep an online (max, sum-exp) over the NEGATIVE columns.
-//   finalize      : one block; merges the per-CTA partials, evaluates the positives with exact fp32 dot
-//                   products, and emits the per-positive losses/weights, the saved row statistics and the
+//   tail          : the LAST CTA of a query block to finish (ticket counter) merges that block's per-CTA partials
+//                   (coalesced: one thread per row), evaluates the positives with exact fp32 dot products and emits the
+//                   per-positive losses / weights and the saved row statistics; the last CTA overall then reduces the
 //                   five scalars the reference computes every step (loss, softmax weight, accuracy, cosine_sim,
-//                   cosine_sim_neg_max) with a fixed (deterministic) reduction order.
+//                   cosine_sim_neg_max) in a fixed (deterministic) order.  No finalize / scalars launches.
 //
-// Operands are fp32 values pre-rounded (round-to-nearest) to TF32 so that the tensor core's truncation of
-// the low 13 mantissa bits is exact: queries/keys are rounded by a tiny pre-pass into the workspace, the
-// queue by its owner at enqueue time (`queue_tf32`, see StorageQueue); positives use the un-rounded data.
+// Operands are fp32 values rounded (to nearest) to TF32 so that the tensor core's truncation of the low 13 mantissa
+// bits is exact: the queue by its owner at enqueue time (`queue_tf32`, see StorageQueue); queries and keys by the
+// epilogue threads, in place in shared memory, right after their TMA tiles land (no pre-pass, no rounded copies in
+// HBM); positives use the un-rounded data.
 #include <math.h>
 
 #include "common.cuh"
@@ -34,7 +37,34 @@ struct NceParams {
   int num_stages;
   float scale_log2;
   float2* partials;
+  // fused tail
+  unsigned int* counters;          // [nmb + 1], zero at launch: per-query-block tickets, then the block-level ticket
+  const float* q;                  // exact fp32 operands for the positives
+  const float* keys;
+  int nP;
+  float temperature;
+  float* dists;
+  float* weights;
+  float* pos_sim;
+  float* neg_max;
+  float* row_lse;
+  float* scalars;
 };
+
+__device__ __forceinline__ uint32_t rna_tf32(uint32_t v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(__uint_as_float(v)));
+  return u;
+}
+// round a shared-memory tile of fp32 to TF32 in place (128 epilogue threads; element-wise, so the swizzle is irrelevant)
+__device__ __forceinline__ void round_tile_tf32(uint8_t* tile, uint32_t bytes, int etid) {
+  uint4* v = reinterpret_cast<uint4*>(tile);
+  for (uint32_t i = etid; i < bytes / 16; i += 128) {
+    uint4 x = v[i];
+    x.x = rna_tf32(x.x), x.y = rna_tf32(x.y), x.z = rna_tf32(x.z), x.w = rna_tf32(x.w);
+    v[i] = x;
+  }
+}
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -58,7 +88,10 @@ __global__ void __launch_bounds__(NCE_THREADS, 1) infonce_main_kernel(const __gr
   uint64_t* tmem_full = empty_bar + NCE_MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* q_full = tmem_empty + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(q_full + 1);
+  uint64_t* q_ready = q_full + 1;                      // queries rounded to TF32 in place (128 arrivals)
+  uint64_t* key_ready = q_ready + 1;                   // one phase per key tile: rounded in place (128 arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(key_ready + 1);
+  uint32_t* flags = tmem_ptr + 1;                      // [2]: last CTA of the query block / last CTA overall
 
   const int m_blk = blockIdx.x % p.nmb;
   const int sidx = blockIdx.x / p.nmb;
@@ -79,6 +112,8 @@ __global__ void __launch_bounds__(NCE_THREADS, 1) infonce_main_kernel(const __gr
       mbar_init(&tmem_empty[s], 128);
     }
     mbar_init(q_full, 1);
+    mbar_init(q_ready, 128);
+    mbar_init(key_ready, 128);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -120,7 +155,7 @@ __global__ void __launch_bounds__(NCE_THREADS, 1) infonce_main_kernel(const __gr
   } else if (warp == 1) {
     if (t_end > t_begin) {
       constexpr uint32_t idesc = make_idesc(UMMA_FMT_TF32, NCE_BM, NCE_BN);
-      mbar_wait(q_full, 0);
+      mbar_wait(q_ready, 0);
       tc_fence_after_sync();
       const uint32_t q_addr = smem_u32(q_smem);
       int stage = 0;
@@ -129,7 +164,8 @@ __global__ void __launch_bounds__(NCE_THREADS, 1) infonce_main_kernel(const __gr
         const int acc = lt & 1;
         const uint32_t acc_phase = (lt >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        mbar_wait(&full_bar[stage], phase);
+        if (t < p.nkt) mbar_wait(key_ready, (uint32_t)(t - t_begin) & 1u);     // key tiles come first: lt == t - t_begin
+        else mbar_wait(&full_bar[stage], phase);
         tc_fence_after_sync();
         const uint32_t st = smem_u32(stages + (size_t)stage * stage_bytes);
         const uint32_t d_tmem = tmem_base + acc * NCE_BN;
@@ -161,10 +197,26 @@ __global__ void __launch_bounds__(NCE_THREADS, 1) infonce_main_kernel(const __gr
     float nmax = -INFINITY;                           // running max of raw similarities over negatives
     float Z = 0.f;                                    // sum exp2((sigma - nmax) * scale_log2) over negatives
     const float c = p.scale_log2;
+    const int etid = threadIdx.x - 64;
+    if (t_end > t_begin) {
+      // queries: exact fp32 from HBM -> TF32 (round to nearest) in place, then visible to the tensor core (async proxy)
+      mbar_wait(q_full, 0);
+      round_tile_tf32(q_smem, q_bytes, etid);
+      fence_proxy_async_smem();
+      mbar_arrive(q_ready);
+    }
     for (int t = t_begin, lt = 0; t < t_end; ++t, ++lt) {
       const int acc = lt & 1;
       const uint32_t acc_phase = (lt >> 1) & 1;
       const bool is_key = t < p.nkt;
+      if (is_key) {
+        // key tiles (the first nkt tiles) arrive un-rounded too: same in-place treatment before the MMA may read them
+        const int stage = lt % p.num_stages;
+        mbar_wait(&full_bar[stage], (uint32_t)(lt / p.num_stages) & 1u);
+        round_tile_tf32(stages + (size_t)stage * stage_bytes, stage_bytes, etid);
+        fence_proxy_async_smem();
+        mbar_arrive(key_ready);
+      }
       const int j0 = (is_key ? t : t - p.nkt) * NCE_BN;
       const int limit = is_key ? p.Bk : p.K;
       const bool needs_mask = is_key || (j0 + NCE_BN > limit);
@@ -208,6 +260,84 @@ __global__ void __launch_bounds__(NCE_THREADS, 1) infonce_main_kernel(const __gr
       }
     }
     p.partials[((size_t)m_blk * p.slices + sidx) * NCE_BM + r] = make_float2(nmax, Z);
+
+    // ---------------- fused tail: last CTA of this query block finalizes its 128 rows ----------------
+    __threadfence();
+    named_bar_sync(1, 128);
+    if (etid == 0) flags[0] = (atomicAdd(&p.counters[m_blk], 1u) == (unsigned)p.slices - 1u) ? 1u : 0u;
+    named_bar_sync(1, 128);
+    if (flags[0]) {
+      __threadfence();
+      if (i < p.B) {
+        const float2* part = p.partials + (size_t)m_blk * p.slices * NCE_BM + r;
+        float gmax = -INFINITY;
+        for (int s_ = 0; s_ < p.slices; ++s_) gmax = fmaxf(gmax, __ldcg(&part[(size_t)s_ * NCE_BM]).x);
+        float Zs = 0.f;
+        for (int s_ = 0; s_ < p.slices; ++s_) {
+          const float2 pr = __ldcg(&part[(size_t)s_ * NCE_BM]);
+          if (pr.x != -INFINITY) Zs += pr.y * exp2f((pr.x - gmax) * c);
+        }
+        // positives: exact fp32 dot products (vince_model.py:213-233 computes them in fp32)
+        const int pos0 = p.nf > 0 ? (i / p.nf) * p.nf : i;
+        float zmax = (gmax == -INFINITY) ? -INFINITY : gmax / p.temperature;
+        float sig[8];
+        const float4* qr = reinterpret_cast<const float4*>(p.q + (size_t)i * p.D);
+        for (int pp = 0; pp < p.nP; ++pp) {
+          const float4* kr = reinterpret_cast<const float4*>(p.keys + (size_t)(pos0 + pp) * p.D);
+          float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+          for (int e = 0; e < p.D / 4; ++e) {
+            const float4 a = __ldg(&qr[e]), b = __ldg(&kr[e]);
+            d0 = fmaf(a.x, b.x, d0), d1 = fmaf(a.y, b.y, d1), d2 = fmaf(a.z, b.z, d2), d3 = fmaf(a.w, b.w, d3);
+          }
+          sig[pp] = (d0 + d1) + (d2 + d3);
+          zmax = fmaxf(zmax, sig[pp] / p.temperature);
+        }
+        // Zneg relative to the row max over ALL columns (loss_util.py:24)
+        const float Zn = (gmax == -INFINITY) ? 0.f : Zs * expf(gmax / p.temperature - zmax);
+        for (int pp = 0; pp < p.nP; ++pp) {
+          const float sp = sig[pp] / p.temperature - zmax;
+          const float logsm = sp - logf(expf(sp) + Zn);
+          p.dists[(size_t)i * p.nP + pp] = -logsm;
+          p.weights[(size_t)i * p.nP + pp] = expf(logsm);
+          p.pos_sim[(size_t)i * p.nP + pp] = sig[pp];
+        }
+        p.neg_max[i] = gmax;
+        p.row_lse[2 * i] = zmax;
+        p.row_lse[2 * i + 1] = Zn;
+      }
+      // ---------------- last CTA overall: the five scalars, fixed reduction order ----------------
+      __threadfence();
+      named_bar_sync(1, 128);
+      if (etid == 0) flags[1] = (atomicAdd(&p.counters[p.nmb], 1u) == (unsigned)p.nmb - 1u) ? 1u : 0u;
+      named_bar_sync(1, 128);
+      if (flags[1]) {
+        __threadfence();
+        float a[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int row = etid; row < p.B; row += 128) {
+          const float nm = __ldcg(&p.neg_max[row]);
+          for (int pp = 0; pp < p.nP; ++pp) {
+            a[0] += __ldcg(&p.dists[(size_t)row * p.nP + pp]);
+            a[1] += __ldcg(&p.weights[(size_t)row * p.nP + pp]);
+            const float ps = __ldcg(&p.pos_sim[(size_t)row * p.nP + pp]);
+            a[2] += ps > nm ? 1.f : 0.f;
+            a[3] += ps;
+          }
+          a[4] += nm;
+        }
+        float* red = reinterpret_cast<float*>(stages);      // the operand ring is idle by now: [5][4] warp partials
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+          if (lane == 0) red[k * 4 + quarter] = a[k];
+        }
+        named_bar_sync(1, 128);
+        if (etid < 5) {
+          const float tot = (red[etid * 4 + 0] + red[etid * 4 + 1]) + (red[etid * 4 + 2] + red[etid * 4 + 3]);
+          p.scalars[etid] = tot / (etid == 4 ? (float)p.B : (float)p.B * (float)p.nP);
+        }
+      }
+    }
   }
 
   tc_fence_before_sync();
@@ -215,18 +345,6 @@ __global__ void __launch_bounds__(NCE_THREADS, 1) infonce_main_kernel(const __gr
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 2 * NCE_BN);
-  }
-}
-
-// round-to-nearest fp32 -> tf32 of two arrays in one launch (queries and keys of the fused loss)
-__global__ void round_tf32_pair_kernel(const float* __restrict__ x0, float* __restrict__ o0, int64_t n0,
-                                       const float* __restrict__ x1, float* __restrict__ o1, int64_t n1) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += (int64_t)gridDim.x * blockDim.x) {
-    const float v = i < n0 ? x0[i] : x1[i - n0];
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-    if (i < n0) o0[i] = __uint_as_float(u);
-    else o1[i - n0] = __uint_as_float(u);
   }
 }
 
@@ -321,7 +439,9 @@ __global__ void nce_scalars_kernel(const float* __restrict__ dists, const float*
 
 size_t infonce_workspace_bytes(int B, int D) {
   const size_t nmb = (B + NCE_BM - 1) / NCE_BM;
-  const size_t rounded = 2 * nmb * NCE_BM * (size_t)D * sizeof(float);       // q_tf32, keys_tf32 (padded rows)
+  // [partials: nmb x 148 slices x 128 rows float2][ticket counters: nmb + 1]; sized as in ABI v1-v3, which also kept
+  // TF32-rounded copies of q / keys here (now rounded in shared memory by the kernel itself)
+  const size_t rounded = 2 * nmb * NCE_BM * (size_t)D * sizeof(float);
   const size_t partials = nmb * 148 * NCE_BM * sizeof(float2);
   return rounded + partials + 1024;
 }
@@ -341,20 +461,13 @@ int infonce_fwd_launch(const InfoNceDesc& d, cudaStream_t stream) {
 
   const int nmb = (d.B + NCE_BM - 1) / NCE_BM;
   const bool ibc = d.num_frames > 0;
+  VB_REQUIRE((reinterpret_cast<uintptr_t>(d.q) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.keys) & 15) == 0,
+             "infonce: q / keys must be 16-byte aligned (TMA)");
   uint8_t* ws = reinterpret_cast<uint8_t*>(d.workspace);
-  float* q_r = reinterpret_cast<float*>(ws);
-  float* k_r = q_r + (size_t)nmb * NCE_BM * d.D;
-  float2* partials = reinterpret_cast<float2*>(k_r + (size_t)nmb * NCE_BM * d.D);
+  float2* partials = reinterpret_cast<float2*>(ws);
+  unsigned int* counters = reinterpret_cast<unsigned int*>(ws + (size_t)nmb * 148 * NCE_BM * sizeof(float2));
 
   int rc = VB_OK;
-  {
-    const int64_t n0 = (int64_t)d.B * d.D, n1 = ibc ? (int64_t)d.Bk * d.D : 0;
-    int64_t blocks = (n0 + n1 + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    round_tf32_pair_kernel<<<(int)blocks, 256, 0, stream>>>(d.q, q_r, n0, d.keys, k_r, n1);
-    VB_CHECK_CUDA(cudaGetLastError());
-  }
-
   NceParams kp;
   memset(&kp, 0, sizeof(kp));
   kp.B = d.B, kp.Bk = d.Bk, kp.K = d.K, kp.D = d.D, kp.nf = d.num_frames;
@@ -372,13 +485,19 @@ int infonce_fwd_launch(const InfoNceDesc& d, cudaStream_t stream) {
   kp.slices = slices;
   kp.scale_log2 = (float)(1.4426950408889634 / (double)d.temperature);
   kp.partials = partials;
+  kp.counters = counters;
+  kp.q = d.q, kp.keys = d.keys;
+  kp.nP = ibc ? d.num_frames : 1;
+  kp.temperature = d.temperature;
+  kp.dists = d.dists, kp.weights = d.weights, kp.pos_sim = d.pos_sim, kp.neg_max = d.neg_max, kp.row_lse = d.row_lse;
+  kp.scalars = d.scalars;
 
   if (T > 0) {
-    rc = encode_tma_2d(&kp.q_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, q_r, d.D, d.B, (uint64_t)d.D * 4, 32, NCE_BM,
+    rc = encode_tma_2d(&kp.q_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.q, d.D, d.B, (uint64_t)d.D * 4, 32, NCE_BM,
                        CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     if (kp.nkt) {
-      rc = encode_tma_2d(&kp.keys_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, k_r, d.D, d.Bk, (uint64_t)d.D * 4, 32, NCE_BN,
+      rc = encode_tma_2d(&kp.keys_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.keys, d.D, d.Bk, (uint64_t)d.D * 4, 32, NCE_BN,
                          CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }
@@ -389,21 +508,28 @@ int infonce_fwd_launch(const InfoNceDesc& d, cudaStream_t stream) {
     }
     const size_t q_bytes = (size_t)(d.D / 32) * NCE_BM * 128;
     const size_t stage_bytes = (size_t)(d.D / 32) * NCE_BN * 128;
-    const size_t fixed = 1024 + q_bytes + (2 * NCE_MAX_STAGES + 5) * 8 + 16;
+    const size_t fixed = 1024 + q_bytes + (2 * NCE_MAX_STAGES + 7) * 8 + 16;
     int stages = (int)((227 * 1024 - fixed) / stage_bytes);
     if (stages > NCE_MAX_STAGES) stages = NCE_MAX_STAGES;
     VB_REQUIRE(stages >= 2, "infonce: not enough shared memory");
     kp.num_stages = stages;
     const size_t smem = fixed + stages * stage_bytes;
-    VB_CHECK_CUDA(cudaFuncSetAttribute(infonce_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool smem_set[64] = {false};                 // the attribute is per device / context
+    if (dev < 0 || dev >= 64 || !smem_set[dev]) {
+      VB_CHECK_CUDA(cudaFuncSetAttribute(infonce_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      if (dev >= 0 && dev < 64) smem_set[dev] = true;
+    }
+    VB_CHECK_CUDA(cudaMemsetAsync(counters, 0, (size_t)(nmb + 1) * sizeof(unsigned int), stream));
     infonce_main_kernel<<<nmb * slices, NCE_THREADS, smem, stream>>>(kp);
     VB_CHECK_CUDA(cudaGetLastError());
+    return VB_OK;                                       // finalize + scalars happen in the kernel's tail
   }
+  // no column tile at all (K == 0 without inter-batch comparison): positives only
 
   NceFinalizeParams fp;
   fp.q = d.q, fp.keys = d.keys, fp.partials = partials;
   fp.B = d.B, fp.D = d.D, fp.nf = d.num_frames, fp.nP = ibc ? d.num_frames : 1;
-  fp.nmb = nmb, fp.slices = T > 0 ? slices : 0;
+  fp.nmb = nmb, fp.slices = 0;
   fp.temperature = d.temperature, fp.scale_log2 = kp.scale_log2;
   fp.dists = d.dists, fp.weights = d.weights, fp.pos_sim = d.pos_sim, fp.neg_max = d.neg_max, fp.row_lse = d.row_lse;
   fp.scalars = d.scalars;

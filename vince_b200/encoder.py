@@ -147,7 +147,7 @@ class Act:
 
 
 class _Plan:
-    __slots__ = ("launches", "stats", "idx_gather", "idx_scatter", "x_hi", "x_lo", "final", "out_shape", "arena_bytes",
+    __slots__ = ("launches", "replay", "stats", "idx_gather", "idx_scatter", "x_hi", "x_lo", "final", "out_shape", "arena_bytes",
                  "n_static", "tape", "shape", "last_input", "last_gather")
 
 
@@ -193,6 +193,7 @@ class EncoderRunner:
         # (measured on B200, profiles/r02_summary.md: bit-identical results but 5 % slower on ResNet-50 - the expansions
         #  are bound by the epilogue's shared-memory traffic, not by the HBM write, so it is off by default)
         self.two_pass = int(os.environ.get("VINCE_B200_TWOPASS", "0"))
+        self.tstats = int(os.environ.get("VINCE_B200_TSTATS", "1"))     # 0: statistics pass in the untransposed form
         # eval mode: BatchNorm(+residual)+ReLU folded into the producing convolution's epilogue (0 = separate bn_apply)
         self.fold_eval = int(os.environ.get("VINCE_B200_FOLD_EVAL", "1"))
 
@@ -202,7 +203,7 @@ class EncoderRunner:
         import copy
         new = EncoderRunner(copy.deepcopy(self.model, memo), self.passes)
         new.block_n_override = self.block_n_override
-        new.two_pass, new.fold_eval = self.two_pass, self.fold_eval
+        new.two_pass, new.fold_eval, new.tstats = self.two_pass, self.fold_eval, self.tstats
         new.input_mean, new.input_std = self.input_mean, self.input_std
         return new
 
@@ -284,7 +285,9 @@ class EncoderRunner:
             self._last_unit["out"] = out
             return out, P, Q
         if train:
-            launches.append(ops.build_conv_fwd(act.hi, act.lo, w_hi, w_lo, None, M, C, spec.K, stats_only=True,
+            # statistics pass: transposed form (channels on the accumulator rows) for plain GEMMs
+            so = 2 if (geom is None and self.tstats) else 1
+            launches.append(ops.build_conv_fwd(act.hi, act.lo, w_hi, w_lo, None, M, C, spec.K, stats_only=so,
                                                **common, **self._bn_args(spec, work, train)))
         hi, lo = self._planes(arena, M, C)
         kw = {}
@@ -392,6 +395,7 @@ class EncoderRunner:
             arena.free(raw_ds, act.hi, act.lo)
             act = nxt
         plan.launches = launches
+        plan.replay = ops.GraphReplay(launches, pre=stats.zero_ if train else None)
         plan.arena_bytes = arena.total
         plan.n_static = len(launches)
         plan.tape = dict(stem=tape_stem, blocks=tape_blocks, pool_out=tape_blocks[0]["input"]) if tape else None
@@ -431,7 +435,7 @@ class EncoderRunner:
             self.bank.refresh()
             tape = bool(tape and train)
             two_pass = 0 if tape else self.two_pass        # the backward reads the raw tensors: no recompute route
-            key = (N, H, W, bool(train), two_pass, self.fold_eval, tape, dev.index, self.bank.generation)
+            key = (N, H, W, bool(train), two_pass, self.tstats, self.fold_eval, tape, dev.index, self.bank.generation)
             if self._plans and next(iter(self._plans))[-1] != self.bank.generation:
                 self._plans.clear()                         # parameters moved: every cached pointer is stale
             plan = self._plans.get(key)
@@ -444,8 +448,6 @@ class EncoderRunner:
                 finally:
                     self.two_pass = saved_tp
                 self._plans[key] = plan
-            if train:
-                plan.stats.zero_()
             gi = si = None
             if gather_idx is not None:
                 plan.idx_gather.copy_(gather_idx)
@@ -457,8 +459,7 @@ class EncoderRunner:
                 ops.build_stem_pack_u8(x, gi, plan.x_hi, plan.x_lo, self.input_mean, self.input_std, grid=patch_grid)()
             else:
                 ops.build_stem_pack(x, gi, plan.x_hi, plan.x_lo, grid=patch_grid)()
-            for run in plan.launches:
-                run()
+            plan.replay()                                   # (zeroes the BN work buffer first in train mode)
             f = plan.final
             spatial = torch.empty(plan.out_shape, device=dev, dtype=torch.float32) if want_spatial else None
             pooled = torch.empty((N, f["C"]), device=dev, dtype=torch.float32)

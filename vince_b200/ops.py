@@ -16,6 +16,56 @@ BN_EPS = 1e-5
 PROFILE = None      # set to a list by bench.py to collect (name, algorithmic flops, start_event, end_event)
 
 
+class GraphReplay:
+    """A static launch list (pre-marshalled closures that all launch on torch's current stream, touch only buffers
+    that stay allocated, and make no allocation or synchronisation) replayed as ONE CUDA graph launch: the first call
+    runs the list eagerly (module loading, cudaFuncSetAttribute and other one-time work must not happen under stream
+    capture), the second captures it, later calls replay the graph.  Per-launch host cost drops from one ctypes call
+    per kernel to one cudaGraphLaunch per list, and the device sees no launch gaps.
+    VINCE_B200_GRAPH=0 (or a bench.py PROFILE run, which wants events around single launches) keeps the eager path."""
+    enabled = None
+
+    def __init__(self, launches, pre=None):
+        self.launches = launches
+        self.pre = pre                  # optional callable run (and captured) before the launches, e.g. a memset
+        self.graph = None
+        self.calls = 0
+        if GraphReplay.enabled is None:
+            import os
+            GraphReplay.enabled = os.environ.get("VINCE_B200_GRAPH", "1") != "0"
+
+    def _eager(self):
+        if self.pre is not None:
+            self.pre()
+        for run in self.launches:
+            run()
+
+    def __call__(self):
+        if not GraphReplay.enabled or PROFILE is not None or not self.launches:
+            return self._eager()
+        if self.graph is not None:
+            return self.graph.replay()
+        self.calls += 1
+        if self.calls < 2 or torch.cuda.is_current_stream_capturing():
+            return self._eager()
+        cur = torch.cuda.current_stream()
+        g = torch.cuda.CUDAGraph()
+        try:
+            # capture on a side stream that first waits for the caller's stream (torch.cuda.graph does both), then replay
+            # on the caller's stream: capture itself executes nothing
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._eager()
+        except Exception:
+            GraphReplay.enabled = False      # e.g. a driver without the needed capture support: stay eager, loudly once
+            import warnings
+            warnings.warn("vince_b200: CUDA graph capture failed, replaying launch lists eagerly")
+            torch.cuda.synchronize()
+            return self._eager()
+        self.graph = g
+        with torch.cuda.stream(cur):
+            g.replay()
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -75,7 +125,8 @@ def build_conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, bl
                    bn_save=False, alpha_dev=None, kchunk=0, taps=1, shift_w=0):
     """geom=None: A is [M,K]; else dict(batch,H,W,Cin,R,S,stride,pad_lo_h,pad_lo_w,pad_hi_h,pad_hi_w) (NHWC gather).
     bn/coef/counter (with stats): fuse the train-mode BatchNorm finalize of module `bn` into the kernel tail.
-    stats_only: statistics pass (nothing stored; `out` may be None).
+    stats_only: statistics pass (nothing stored; `out` may be None); 2 = the transposed form (channels along the
+    accumulator rows: sums are in-register adds), available when geom is None (1x1 stride-1 convolutions).
     out_planes=(hi, lo) with ep_coef [2N]: "apply" epilogue - planes = relu?(acc*scale + shift + residual), residual =
     res_planes (hi, lo) or bn(res_raw) with res_coef; `out` must be None."""
     d = _lib.ConvDesc()
@@ -103,7 +154,7 @@ def build_conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, bl
     d.stats = _val(stats, torch.float64, "stats")
     d.halo_mode = halo_mode
     d.alpha = float(alpha)
-    d.stats_only = 1 if stats_only else 0
+    d.stats_only = int(stats_only)          # 0 | 1 statistics pass | 2 transposed statistics pass (plain GEMMs only)
     d.bn_save = 1 if bn_save else 0
     d.alpha_dev = _val(alpha_dev, torch.float32, "alpha_dev")
     d.kchunk, d.taps, d.shift_w = int(kchunk), int(taps), int(shift_w)
