@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== pytest"; timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 | tee gpurun_out/pytest_gpu_p.log
+{
+echo "== conv apply 1"; python tests/conv_bench.py --filter "r50.layer" --iters 7 --apply 1
+echo "== conv apply 2"; python tests/conv_bench.py --filter "r50.layer" --iters 7 --apply 2
+echo "== conv apply 1 EPI_SETS=1"; VINCE_B200_EPI_SETS=1 python tests/conv_bench.py --filter "r50.layer" --iters 7 --apply 1
+} 2>&1 | tee gpurun_out/conv_variants_p.log
+for v in "0" "1"; do
+echo "== bench --config 2 TWOPASS=$v"; VINCE_B200_TWOPASS=$v timeout 600 python bench.py --config 2 --steps 20 --warmup 5 --no-train --no-ref-gpu 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'roof', d['roofline']['frac'], 'nce', d['infonce_step_ms'], d['infonce_step_with_dq_backward_ms'], d['clocks'])"
+done
+python tests/nce_host_probe.py ResNet50 2>&1 | head -3

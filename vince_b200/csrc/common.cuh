@@ -112,6 +112,17 @@ __device__ __forceinline__ void two_sum_acc(float& s, float& e, float x) {
   s = t;
 }
 
+// 32 bytes from global memory in one request (sm_100 256-bit load), read-only path, no L1 allocation, L2 asked to fetch the
+// surrounding 256 bytes: for streams whose neighbours are wanted a little later by the same SM (`p` 32-byte aligned)
+__device__ __forceinline__ void ldg256_stream(const void* p, uint32_t* r) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+
+// fire-and-forget request to bring the 128-byte line holding `p` into L2
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

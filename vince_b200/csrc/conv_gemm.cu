@@ -41,10 +41,6 @@ constexpr size_t SMEM_BUDGET = 226 * 1024;    // of 227 KB: leaves the 1 KB syst
 struct GemmKernelParams {
   CUtensorMap a_hi, a_lo, b_hi, b_lo, out;
   CUtensorMap out_hi, out_lo;    // EPI == 1: fp16 (hi, lo) output planes (box 32 channels x 128 rows, SWIZZLE_64B)
-  CUtensorMap res_a, res_b;      // EPI == 1 residual tiles, same boxes as the output: (hi, lo) planes (res_kind 1) or
-                                 // res_a = the raw fp32 tensor (res_kind 2; box 32 x 128 fp32, SWIZZLE_128B)
-  int res_bufs;                  // residual tiles in flight (TMA ring depth, <= 4)
-  uint32_t res_tx_bytes;         // bytes one residual tile delivers (both planes)
   int staging_bufs;              // output staging tiles in shared memory (1 or 2)
   uint32_t staging_total;        // bytes of the staging area: staging_bufs output tiles (+ 2 residual tiles, EPI == 1)
   // EPI == 1 ("apply" epilogue): out = relu?( acc*alpha*coef[c] + coef[N+c] + residual ) split into fp16 planes
@@ -143,8 +139,13 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 // output channels from the weight matrix, kernel columns = pixels), so an accumulator ROW holds one channel over BN
 // pixels and a thread's tcgen05.ld delivers 32 values of ITS channel - BatchNorm sum / sum of squares are then plain
 // in-register adds (no staging tile, no barrier, no cross-thread reduction) and nothing is stored at all.
-template <int BN, int CG, bool HALO, bool RES, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
+// EW = number of epilogue warp SETS (4 warps each, one per TMEM lane quarter).  The epilogue of the small-K layers is
+// latency-bound with one warp per scheduler (issue slots ~25 % busy, ~1500-2900 cycles per 32-column chunk); with EW = 2
+// the sets work on alternate chunks of a tile, each with its own staging tile, store leader and named barriers.
+template <int BN, int CG, bool HALO, bool RES, int EPI, int EW>
+__global__ void __launch_bounds__(GEMM_THREADS + 128 * (EW - 1), (EW == 1 && EPI != 1) ? 2 : 1)
+conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
+  constexpr int ETHREADS = 128 * EW;               // epilogue threads
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -169,8 +170,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
   uint64_t* b_empty = b_full + MAX_RING;
   uint64_t* tmem_full = b_empty + MAX_RING;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_full = tmem_empty + 2;             // [4] residual tile ring (EPI == 1)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 4);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   uint32_t* last_flag = tmem_ptr + 1;
   double* smem_stats = reinterpret_cast<double*>(tmem_ptr + 2);     // [4 epilogue warps][2][BN], warp-private
 
@@ -180,8 +180,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
     if (EPI == 1) {
       tma_prefetch_desc(&p.out_hi);
       tma_prefetch_desc(&p.out_lo);
-      if (p.res_kind != 0) tma_prefetch_desc(&p.res_a);
-      if (p.res_kind == 1 && p.res_lo != nullptr) tma_prefetch_desc(&p.res_b);
     } else if (EPI == 0) {
       tma_prefetch_desc(&p.out);
     }
@@ -204,9 +202,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], CG == 2 ? 8 : 128);    // pair: one arrive per epilogue warp of both CTAs
+      mbar_init(&tmem_empty[s], CG == 2 ? 8 * EW : ETHREADS);    // pair: one arrive per epilogue warp of both CTAs
     }
-    for (int s = 0; s < 4; ++s) mbar_init(&res_full[s], 1);
     fence_mbar_init();
   }
   if (warp == 4) {
@@ -219,7 +216,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
     }
   }
   if (EPI == 0 && threadIdx.x >= EPI_TID0) {       // (EPI 1 keeps 4 x BN coefficients there, EPI 2 nothing)
-    for (int i = threadIdx.x - EPI_TID0; i < 8 * BN + 2; i += 128) smem_stats[i] = 0.0;
+    for (int i = threadIdx.x - EPI_TID0; i < 8 * BN + 2; i += ETHREADS) smem_stats[i] = 0.0;
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -489,9 +486,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
     // round-1 scheme (wait for the store, barrier, write, barrier) is kept.
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
-    const int etid = threadIdx.x - EPI_TID0;       // 0..127
+    const int etid = threadIdx.x - EPI_TID0;       // 0..ETHREADS-1
+    const int eset = etid >> 7;                    // epilogue warp set of this thread
+    const int ltid = etid & 127;                   // thread index inside the set
+    const uint32_t bar_a = 2u + 2u * (uint32_t)eset, bar_b = 3u + 2u * (uint32_t)eset;     // the set's named barriers
     const uint32_t staging_s = smem_u32(staging);
-    const int nbuf = p.staging_bufs;               // 1 or 2 output staging tiles
+    const int nbuf = p.staging_bufs;               // output staging tiles in total (EW == 2: one per set)
+    const bool one_tile = (EW == 2) || nbuf == 1;  // this set cycles through a single staging tile
     // kernel parameters used per chunk, read once (the asm barriers would otherwise force constant-bank re-reads)
     const bool has_stats = (EPI != 1) && p.stats != nullptr;
     const bool do_store = p.stats_only == 0;
@@ -500,12 +501,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
     const long long M = p.M;
     const int relu = p.relu;
     const int res_kind = (EPI == 1) ? p.res_kind : 0;
-    const bool store_leader = (etid == 0);
+    const bool store_leader = (ltid == 0);
     bool store_pending = false;
     const float* const ep_scale = p.scale;
     const float* const ep_bias = p.bias;
     const uint32_t stats_s = smem_u32(smem_stats + 1);        // 16-byte aligned: [4 warps][BN] x {sum, err, sq, err}
-    const uint32_t res_s = staging_s + (uint32_t)nbuf * STAGING_BYTES;      // EPI == 1: the residual tile ring
     // halo mode: which output pixel (if any) this accumulator row is
     int hy = 0, hx = 0;
     if (HALO) {
@@ -514,7 +514,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
     }
     int local_t = 0;
     int cur_n_blk = -1;
-    uint32_t chunk_ctr = 0;
     uint32_t tmem_empty_leader[2] = {0u, 0u};
     if (CG == 2) {
       tmem_empty_leader[0] = mapa_shared(smem_u32(&tmem_empty[0]), 0);
@@ -536,34 +535,39 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
       }
       if (m0 + nvalid > M) nvalid = (int)(M - m0 > 0 ? M - m0 : 0);
     };
-    // EPI == 1: the residual tile of every chunk is fetched by TMA (one elected thread, same box and swizzle as the
-    // output tile, so the row-owner reads below are bank-conflict free) into a ring of `res_bufs` tiles: with a single
-    // tile in flight per SM the residual stream was latency-bound (16 KB x 148 SMs in flight ~ 1.6 TB/s); chunk k of this
-    // CTA (counted across tiles) uses tile k % res_bufs and phase (k / res_bufs) & 1 of its barrier.
+    // EPI == 1: the residual of a chunk goes straight from global memory into the row owner's registers - its 32 channels
+    // are 64 contiguous bytes per fp16 plane (128 bytes of the raw fp32 tensor), fetched with 256-bit loads that bypass L1
+    // and ask L2 for the whole 256-byte neighbourhood the following chunks of the tile will want.  The loads for the
+    // set's NEXT chunk are issued as soon as the current ones are consumed.  (Two earlier schemes were slower: cp.async
+    // tiles one chunk ahead; and TMA tiles through an mbarrier ring, which queue in the SM's TMA unit behind the output
+    // stores - in a write-bound kernel every residual load then waited for the store ahead of it, ncu: half of the
+    // epilogue's samples on that barrier, reads and writes serialised at ~480 us for the 56x56 64->256 layer.)
     constexpr int CHUNKS = BN / 32;
-    const int rbufs = p.res_bufs;
-    auto issue_residual = [&](uint32_t k) {
-      const int tile = tile_start + (int)(k / CHUNKS) * tile_step;
-      if (tile >= num_tiles) return;
-      const int chunk = (int)(k % CHUNKS);
-      const int tb = tile % p.tiles_per_batch;
-      const int m_blk = (tb % p.num_m_blocks) * CG + (int)cta_rank;
-      const int c0 = (tb / p.num_m_blocks) * BN + chunk * 32;
-      const uint32_t b = k % (uint32_t)rbufs;
-      uint8_t* dst = staging + (size_t)(nbuf + (int)b) * STAGING_BYTES;
-      mbar_expect_tx(&res_full[b], p.res_tx_bytes);
-      if (HALO) {
-        const int img = m_blk / p.tiles_per_img;
-        const int y0 = (m_blk - img * p.tiles_per_img) * p.TH;
-        tma_load_4d(dst, &p.res_a, &res_full[b], c0, 0, y0, img);
-        if (res_kind == 1 && p.res_lo != nullptr) tma_load_4d(dst + 8192, &p.res_b, &res_full[b], c0, 0, y0, img);
+    uint32_t rres[32];
+    const bool row_ok0 = HALO ? ((hy < p.TH) && (hx < p.W)) : true;
+    const int srow0 = HALO ? hy * p.W + hx : row;
+    auto load_residual = [&](int tile, int chunk) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) rres[i] = 0u;
+      if (res_kind == 0 || tile >= num_tiles) return;
+      long long m0;
+      int nvalid, n_blk;
+      tile_rows(tile, m0, nvalid, n_blk);
+      if (!(row_ok0 && srow0 < nvalid)) return;
+      const long long e = (m0 + srow0) * N + n_blk * BN + chunk * 32;
+      if (res_kind == 1) {
+        ldg256_stream(p.res_hi + e, &rres[0]);
+        ldg256_stream(p.res_hi + e + 16, &rres[8]);
+        if (p.res_lo != nullptr) {
+          ldg256_stream(p.res_lo + e, &rres[16]);
+          ldg256_stream(p.res_lo + e + 16, &rres[24]);
+        }
       } else {
-        tma_load_2d(dst, &p.res_a, &res_full[b], c0, m_blk * BM);
-        if (res_kind == 1 && p.res_lo != nullptr) tma_load_2d(dst + 8192, &p.res_b, &res_full[b], c0, m_blk * BM);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ldg256_stream(p.res_raw + e + 8 * j, &rres[8 * j]);
       }
     };
-    if (EPI == 1 && res_kind != 0 && store_leader)
-      for (int k = 0; k < rbufs; ++k) issue_residual((uint32_t)k);
+    if (EPI == 1) load_residual(tile_start, eset);
     if (EPI == 2) {
       // ---- transposed statistics pass: this thread owns channel (m_blk * 128 + row) of every tile it sees ----
       const int NC = p.stat_channels;
@@ -589,11 +593,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after_sync();
 #pragma unroll 1
-        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        for (int chunk = eset; chunk < BN / 32; chunk += EW) {
           uint32_t raw[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk * 32, raw);
           tmem_ld_wait();
-          if (chunk == BN / 32 - 1) {
+          if (chunk + EW >= BN / 32) {
             tc_fence_before_sync();
             if (CG == 2) {
               __syncwarp();
@@ -637,12 +641,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
         srow = hy * p.W + hx;
       }
       valid = valid && srow < nvalid;
+      if (EPI == 1 && res_kind != 0 && tile + tile_step < num_tiles) {
+        // the residual rows of this CTA's NEXT tile: ask L2 for them now, a whole tile time before the 256-bit loads
+        // above want them (those are issued only one chunk ahead, less than a DRAM round trip under load)
+        long long m0n;
+        int nvn, nbn;
+        tile_rows(tile + tile_step, m0n, nvn, nbn);
+        if (row_ok0 && srow0 < nvn) {
+          const long long e = (m0n + srow0) * N + nbn * BN;
+          if (res_kind == 1) {
+            for (int l = eset; l < BN / 64; l += EW) {
+              prefetch_l2(p.res_hi + e + 64 * l);
+              if (p.res_lo != nullptr) prefetch_l2(p.res_lo + e + 64 * l);
+            }
+          } else {
+            for (int l = eset; l < BN / 32; l += EW) prefetch_l2(p.res_raw + e + 32 * l);
+          }
+        }
+      }
       if (EPI == 1 && n_blk != cur_n_blk) {
         // per-channel coefficients of this n-block, cached in the (otherwise unused) statistics area:
         // [0,BN) scale  [BN,2BN) shift  [2BN,3BN) residual scale  [3BN,4BN) residual shift
         float* cf = reinterpret_cast<float*>(smem_stats + 1);      // +8 bytes: 16-byte aligned for the vector reads
-        named_bar_sync(1, 128);                    // readers of the previous n-block's coefficients are done
-        for (int i = etid; i < BN; i += 128) {
+        named_bar_sync(1, ETHREADS);                    // readers of the previous n-block's coefficients are done
+        for (int i = etid; i < BN; i += ETHREADS) {
           const int c = n_blk * BN + i;
           const bool ok = c < N;
           cf[i] = ok ? __ldg(p.ep_coef + c) : 0.f;
@@ -652,13 +674,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
             cf[3 * BN + i] = ok ? __ldg(p.res_coef + N + c) : 0.f;
           }
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, ETHREADS);
         cur_n_blk = n_blk;
       }
       if (has_stats && n_blk != cur_n_blk) {
         if (cur_n_blk >= 0) {
-          named_bar_sync(1, 128);
-          for (int i = etid; i < BN; i += 128) {
+          named_bar_sync(1, ETHREADS);
+          for (int i = etid; i < BN; i += ETHREADS) {
             double a = 0.0, b = 0.0;
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
@@ -673,7 +695,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
               atomicAdd(&p.stats[N + cur_n_blk * BN + i], b);
             }
           }
-          named_bar_sync(1, 128);
+          named_bar_sync(1, ETHREADS);
         }
         cur_n_blk = n_blk;
       }
@@ -681,14 +703,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
       tc_fence_after_sync();
       if (etid == 0) VB_TRACE_EVENT(3, local_t);
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk, ++chunk_ctr) {
+      for (int chunk = eset; chunk < BN / 32; chunk += EW) {
+        const uint32_t chunk_ctr = (uint32_t)local_t * (uint32_t)(BN / 32) + (uint32_t)chunk;   // chunk index in this CTA
         const int c0 = n_blk * BN + chunk * 32;
-        const uint32_t buf = staging_s + (nbuf == 2 ? (chunk_ctr & 1u) * STAGING_BYTES : 0u);
+        const uint32_t buf = staging_s + (EW == 2 ? (uint32_t)eset : (nbuf == 2 ? (chunk_ctr & 1u) : 0u)) * STAGING_BYTES;
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk * 32, raw);
         tmem_ld_wait();
-        if (chunk == BN / 32 - 1) {
-          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+        if (chunk + EW >= BN / 32) {
+          // all TMEM reads of this accumulator (by this set) are done: hand it back to the MMA warp
           tc_fence_before_sync();
           if (CG == 2) {
             // the leader's MMA warp owns both accumulators: one remote arrive per epilogue warp
@@ -699,14 +722,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
           }
         }
         if (EPI == 1) {
-          const uint32_t rslot = chunk_ctr % (uint32_t)rbufs;
-          const uint32_t rcur = res_s + rslot * STAGING_BYTES;
-          // the residual tile of THIS chunk has landed (TMA, mbarrier); with one output staging tile everybody must
-          // also be done with the previous chunk's tile before it is overwritten
-          if (res_kind != 0) mbar_wait(&res_full[rslot], (chunk_ctr / (uint32_t)rbufs) & 1u);
-          if (nbuf == 1) {
+          // with one output staging tile everybody must be done with the previous chunk's tile before it is overwritten
+          if (one_tile) {
             if (store_leader && store_pending) tma_store_wait_read0();
-            named_bar_sync(2, 128);
+            named_bar_sync(bar_a, 128);
           }
           const uint32_t cfs = stats_s + (uint32_t)(chunk * 32) * 4u;
           // two 8 KB tiles (hi | lo) of 64-byte rows; 16-byte piece j of row `srow` stored at j ^ ((srow >> 1) & 3),
@@ -725,11 +744,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
               v[4 * q + 3] = fmaf(__uint_as_float(raw[8 * g8 + 4 * q + 3]) * alpha, sc.w, sh.w);
             }
             if (res_kind == 1) {
-              const uint32_t off = (uint32_t)(srow * 64 + ((g8 ^ sw) << 4));
-              const float4 fh = valid ? lds_v4(rcur + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-              const float4 fl = (valid && p.res_lo != nullptr) ? lds_v4(rcur + 8192u + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-              const uint32_t hw[4] = {__float_as_uint(fh.x), __float_as_uint(fh.y), __float_as_uint(fh.z), __float_as_uint(fh.w)};
-              const uint32_t lw[4] = {__float_as_uint(fl.x), __float_as_uint(fl.y), __float_as_uint(fl.z), __float_as_uint(fl.w)};
+              const uint32_t hw[4] = {rres[4 * g8], rres[4 * g8 + 1], rres[4 * g8 + 2], rres[4 * g8 + 3]};
+              const uint32_t lw[4] = {rres[16 + 4 * g8], rres[17 + 4 * g8], rres[18 + 4 * g8], rres[19 + 4 * g8]};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const __half2 ha = *reinterpret_cast<const __half2*>(&hw[i]), hb = *reinterpret_cast<const __half2*>(&lw[i]);
@@ -741,13 +757,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
               for (int q = 0; q < 2; ++q) {
                 const float4 rsc = lds_v4(cfs + 2 * BN * 4 + (2 * g8 + q) * 16);
                 const float4 rsh = lds_v4(cfs + 3 * BN * 4 + (2 * g8 + q) * 16);
-                const int pj = 2 * g8 + q;
-                const float4 r4 = valid ? lds_v4(rcur + (uint32_t)(srow * 128 + ((pj ^ (srow & 7)) << 4)))
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-                v[4 * q + 0] += fmaf(r4.x, rsc.x, rsh.x);
-                v[4 * q + 1] += fmaf(r4.y, rsc.y, rsh.y);
-                v[4 * q + 2] += fmaf(r4.z, rsc.z, rsh.z);
-                v[4 * q + 3] += fmaf(r4.w, rsc.w, rsh.w);
+                // (rows that are not output pixels hold zeros and are never stored)
+                v[4 * q + 0] += fmaf(__uint_as_float(rres[8 * g8 + 4 * q + 0]), rsc.x, rsh.x);
+                v[4 * q + 1] += fmaf(__uint_as_float(rres[8 * g8 + 4 * q + 1]), rsc.y, rsh.y);
+                v[4 * q + 2] += fmaf(__uint_as_float(rres[8 * g8 + 4 * q + 2]), rsc.z, rsh.z);
+                v[4 * q + 3] += fmaf(__uint_as_float(rres[8 * g8 + 4 * q + 3]), rsc.w, rsh.w);
               }
             }
             if (relu) {
@@ -772,11 +786,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
                                                      __uint_as_float(lq[2]), __uint_as_float(lq[3])));
             }
           }
+          // this chunk's residual is consumed: fetch the one of this set's next chunk (same tile, or the next tile's first).
+          // (Issued here, before the proxy fence, the fence absorbs part of the load latency - ncu: 25 % of the epilogue's
+          //  samples on fence + barrier - but issuing after the barrier was measured slower still: 497 vs 434 us.)
+          if (res_kind != 0) {
+            if (chunk + EW < CHUNKS) load_residual(tile, chunk + EW);
+            else load_residual(tile + tile_step, eset);
+          }
           fence_proxy_async_smem();
           // two tiles: the PREVIOUS chunk's store (other tile) must have drained before the barrier lets anybody start
           // the next chunk, which overwrites that tile
-          if (nbuf == 2 && store_leader && store_pending) tma_store_wait_read0();
-          named_bar_sync(3, 128);
+          if (!one_tile && store_leader && store_pending) tma_store_wait_read0();
+          named_bar_sync(bar_b, 128);
           if (store_leader) {
             const void* src = staging + (buf - staging_s);
             if (HALO) {
@@ -787,8 +808,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
               if (planes == 2) tma_store_2d(&p.out_lo, reinterpret_cast<const uint8_t*>(src) + 8192, c0, out_row0);
             }
             tma_store_commit();
-            // every thread has passed the barrier, i.e. is done reading this chunk's residual tile: refill it
-            if (res_kind != 0) issue_residual(chunk_ctr + (uint32_t)rbufs);
           }
           store_pending = true;
           continue;
@@ -810,9 +829,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
         }
         // one staging tile: everybody must be done reading the previous chunk before it is overwritten; two tiles:
         // the barrier below (of the previous chunk) already guarantees that for the tile of two chunks ago
-        if (nbuf == 1) {
+        if (one_tile) {
           if (store_leader && store_pending) tma_store_wait_read0();
-          named_bar_sync(2, 128);
+          named_bar_sync(bar_a, 128);
         }
         if (valid) {
           // 128-byte row `srow`, 16-byte piece j stored at (j ^ (srow & 7)): SWIZZLE_128B, conflict-free
@@ -823,9 +842,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
         }
         if (do_store) {
           fence_proxy_async_smem();
-          if (nbuf == 2 && store_leader && store_pending) tma_store_wait_read0();
+          if (!one_tile && store_leader && store_pending) tma_store_wait_read0();
         }
-        named_bar_sync(3, 128);
+        named_bar_sync(bar_b, 128);
         if (do_store) {
           if (store_leader) {
             const void* src = staging + (buf - staging_s);
@@ -872,8 +891,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
     if (store_leader) tma_store_wait0();
     if (has_stats) {
       if (cur_n_blk >= 0) {
-        named_bar_sync(1, 128);
-        for (int i = etid; i < BN; i += 128) {
+        named_bar_sync(1, ETHREADS);
+        for (int i = etid; i < BN; i += ETHREADS) {
           double a = 0.0, b = 0.0;
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
@@ -891,16 +910,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) conv_gemm_kernel(const __grid
         // The last CTA to arrive owns the BatchNorm finalize: batch mean / biased variance -> per-channel
         // scale = gamma / sqrt(var + eps), shift = beta - mean * scale, running stats with the unbiased variance.
         __threadfence();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, ETHREADS);
         if (etid == 0) {
           const unsigned int ticket = atomicAdd(p.bn_counter, 1u);
           *last_flag = (ticket == gridDim.x - 1) ? 1u : 0u;
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, ETHREADS);
         if (*last_flag) {
           __threadfence();
           const int N = p.stat_channels;            // (shadows the kernel's column extent: they differ when EPI == 2)
-          for (int c = etid; c < N; c += 128) {
+          for (int c = etid; c < N; c += ETHREADS) {
             const double mean = __ldcg(&p.stats[c]) / p.bn_count;
             double var = __ldcg(&p.stats[N + c]) / p.bn_count - mean * mean;
             if (var < 0.0) var = 0.0;
@@ -983,35 +1002,35 @@ static int staging_tiles(const ConvGemmDesc& d) {
   if (e && (atoi(e) == 1 || atoi(e) == 2)) nbuf = atoi(e);
   return nbuf;
 }
-// residual tiles of the apply epilogue (TMA ring): as many as fit next to a 2-stage operand ring, at most 4
 static size_t staging_bytes(const ConvGemmDesc& d) {
   if (d.stats_only == 2) return 0;                   // transposed statistics pass: nothing is staged
-  return (size_t)STAGING_BYTES * (staging_tiles(d) + ((d.out_hi != nullptr && d.res_kind != 0) ? (d.res_tiles > 0 ? d.res_tiles : 2) : 0));
+  return (size_t)STAGING_BYTES * staging_tiles(d);
 }
 static size_t fixed_smem(int bn, const ConvGemmDesc& d) {
   // alignment slack + staging + barriers + flags + per-channel area (EPI 0: [4 warps][2][bn] double-float sums,
   // EPI 1: 4 x bn coefficients, EPI 2: unused)
   const size_t chan = d.out_hi != nullptr ? (size_t)4 * bn * 4 + 16 : (d.stats_only == 2 ? 16 : (size_t)8 * bn * 8);
-  return 1024 + staging_bytes(d) + (4 * MAX_RING + 8) * 8 + 32 + chan;
+  return 1024 + staging_bytes(d) + (4 * MAX_RING + 4) * 8 + 32 + chan;
 }
 
-template <int BN, int CG, bool HALO, bool RES, int EPI>
+template <int BN, int CG, bool HALO, bool RES, int EPI, int EW = 1>
 static int launch_gemm(const GemmKernelParams& kp, size_t smem, int grid, cudaStream_t stream) {
   static bool smem_set[MAX_DEVICES] = {false};       // per instantiation AND device (the attribute is per context)
   const int dev = current_device();
+  constexpr int THREADS = GEMM_THREADS + 128 * (EW - 1);
   if (!smem_set[dev]) {
-    VB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, CG, HALO, RES, EPI>,
+    VB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, CG, HALO, RES, EPI, EW>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
     smem_set[dev] = true;
   }
   if (CG == 1) {
-    conv_gemm_kernel<BN, CG, HALO, RES, EPI><<<grid, GEMM_THREADS, smem, stream>>>(kp);
+    conv_gemm_kernel<BN, CG, HALO, RES, EPI, EW><<<grid, THREADS, smem, stream>>>(kp);
   } else {
     grid &= ~1;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -1021,7 +1040,7 @@ static int launch_gemm(const GemmKernelParams& kp, size_t smem, int grid, cudaSt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CG, HALO, RES, EPI>, kp));
+    VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CG, HALO, RES, EPI, EW>, kp));
   }
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
@@ -1041,7 +1060,11 @@ static int auto_block_n(const ConvGemmDesc& d, int cg) {
       // a 2-stage ring of (A tile + this CTA's weight share) must fit next to the fixed buffers
       const size_t planes = d.passes == 3 ? 2 : 1;
       const size_t stage = ((size_t)BM * 128 + (size_t)(bn / cg) * 128) * planes;
-      if (bn > 64 && fixed_smem(bn, d) + 2 * stage > SMEM_BUDGET) continue;
+      // ... or, for a single n-block, the whole weight share resident next to two activation stages (RES mode)
+      const size_t a_st = (size_t)BM * 128 * planes, b_st = (size_t)(bn / cg) * 128 * planes;
+      const bool res_fits = !d.im2col && d.kchunk == 0 && bn >= d.N && m_blocks >= 2 * units &&
+                            fixed_smem(bn, d) + (size_t)(d.K / BK) * b_st + 2 * a_st <= SMEM_BUDGET;
+      if (bn > 64 && !res_fits && fixed_smem(bn, d) + 2 * stage > SMEM_BUDGET) continue;
     }
     long tiles = m_blocks * ((d.N + bn - 1) / bn);
     if (d.kchunk > 0) tiles *= (long)d.taps * ((d.K + d.kchunk - 1) / d.kchunk);     // batched split-K: every batch
@@ -1296,37 +1319,16 @@ int conv_gemm_launch(const ConvGemmDesc& d_in, cudaStream_t stream) {
       if (rc) return rc;
     }
   }
+  // two epilogue warp sets where the epilogue is the bottleneck: few k-blocks per tile (the layers that already get two
+  // staging tiles), never the 3x3 halo path; the transposed statistics pass has no staging at all
+  int ew = ((staging_tiles(d) == 2 || tstats) && kp.a_mode != 2) ? 2 : 1;
+  {
+    const char* e = getenv("VINCE_B200_EPI_SETS");     // debug / A-B comparison: 1 forces a single set
+    if (e && atoi(e) == 1) ew = 1;
+  }
   // ---- shared-memory budget: A ring + B ring ----
   const size_t a_stage = (size_t)kp.a_plane_bytes * planes;
   const size_t b_stage = (size_t)(bn / cg) * 128 * planes;
-  if (planes_out && d.res_kind != 0) {
-    // residual ring: as deep as fits next to a 2-stage operand ring (tile-width / halo decisions above assumed 2)
-    int want = 4;
-    const char* e = getenv("VINCE_B200_RES_TILES");    // debug / A-B comparison: 2..4
-    if (e && atoi(e) >= 2 && atoi(e) <= 4) want = atoi(e);
-    for (d.res_tiles = want; d.res_tiles > 2; --d.res_tiles)
-      if (fixed_smem(bn, d) + 2 * (a_stage + b_stage) <= SMEM_BUDGET) break;
-    kp.res_bufs = d.res_tiles;
-    // same boxes as the output tiles
-    const bool raw = d.res_kind == 2;
-    const CUtensorMapDataType dt = raw ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    const CUtensorMapSwizzle sw = raw ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    const void* ra = raw ? (const void*)d.res_raw : d.res_hi;
-    const bool two = !raw && d.res_lo != nullptr;
-    if (kp.a_mode == 2) {
-      rc = encode_tma_4d_nhwc(&kp.res_a, dt, ra, d.batch, d.H, d.W, d.N, 32, d.W, kp.TH, sw);
-      if (rc) return rc;
-      if (two) rc = encode_tma_4d_nhwc(&kp.res_b, dt, d.res_lo, d.batch, d.H, d.W, d.N, 32, d.W, kp.TH, sw);
-      if (rc) return rc;
-      kp.res_tx_bytes = (uint32_t)(32 * d.W * kp.TH) * (raw ? 4u : (two ? 4u : 2u));
-    } else {
-      rc = encode_tma_2d(&kp.res_a, dt, ra, d.N, d.M, (uint64_t)d.N * (raw ? 4 : 2), 32, BM, sw);
-      if (rc) return rc;
-      if (two) rc = encode_tma_2d(&kp.res_b, dt, d.res_lo, d.N, d.M, (uint64_t)d.N * 2, 32, BM, sw);
-      if (rc) return rc;
-      kp.res_tx_bytes = (uint32_t)(32 * BM) * (raw ? 4u : (two ? 4u : 2u));
-    }
-  }
   kp.staging_bufs = staging_tiles(d);
   kp.staging_total = (uint32_t)staging_bytes(d);
   const size_t avail = SMEM_BUDGET - fixed_smem(bn, d);
@@ -1367,6 +1369,9 @@ int conv_gemm_launch(const ConvGemmDesc& d_in, cudaStream_t stream) {
   const bool halo = kp.a_mode == 2;
   if (cg == 2) grid &= ~1;
   if (tstats) {
+    if (ew == 2)
+      return cg == 2 ? launch_gemm<256, 2, false, false, 2, 2>(kp, smem, grid, stream)
+                     : launch_gemm<256, 1, false, false, 2, 2>(kp, smem, grid, stream);
     return cg == 2 ? launch_gemm<256, 2, false, false, 2>(kp, smem, grid, stream)
                    : launch_gemm<256, 1, false, false, 2>(kp, smem, grid, stream);
   }
@@ -1374,6 +1379,8 @@ int conv_gemm_launch(const ConvGemmDesc& d_in, cudaStream_t stream) {
   {                                                                                             \
     if (halo) return res ? launch_gemm<BN_, CG_, true, true, EPI_>(kp, smem, grid, stream)      \
                          : launch_gemm<BN_, CG_, true, false, EPI_>(kp, smem, grid, stream);    \
+    if (ew == 2) return res ? launch_gemm<BN_, CG_, false, true, EPI_, 2>(kp, smem, grid, stream)    \
+                            : launch_gemm<BN_, CG_, false, false, EPI_, 2>(kp, smem, grid, stream);  \
     return res ? launch_gemm<BN_, CG_, false, true, EPI_>(kp, smem, grid, stream)               \
                : launch_gemm<BN_, CG_, false, false, EPI_>(kp, smem, grid, stream);             \
   }

@@ -94,6 +94,9 @@ def _record_stream_all(obj, stream):
             _record_stream_all(v, stream)
 
 
+_PARAM_EPOCH = [0]      # bumped whenever a BaseModel may have re-allocated its parameters
+
+
 TIME_STR = time.strftime("%Y_%m_%d_%H_%M_%S")     # constants.py:23 (one sub-directory per run, as in the reference)
 
 
@@ -141,6 +144,15 @@ class BaseModel(nn.Module):
     def to(self, device):
         self._device = device
         super().to(device)
+
+    def _apply(self, fn, *a, **k):
+        # .to() / .cuda() / .float() ... may re-allocate parameters: cached device pointers (EMA chunk table) are stale
+        _PARAM_EPOCH[0] += 1
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        _PARAM_EPOCH[0] += 1
+        return super().load_state_dict(*a, **k)
 
     def restore(self, skip_filter=None) -> int:
         """models/base_model.py:13-19 -> dg_util restore_from_folder: load the newest checkpoint found under
@@ -680,13 +692,21 @@ class VinceQueueModel(BaseModel):
         import numpy as np
         # fast path (every training step): same encoder object and EVERY parameter of both encoders still lives where
         # the cached table says (re-allocating a single tensor must not leave the kernel writing through a stale pointer)
+        # (a full scan costs ~0.3 us per tensor - 100 us per step for the 2 x 161 tensors of a ResNet-50, more than the
+        #  EMA kernel itself: every step checks the module-re-allocation epoch (bumped by BaseModel._apply /
+        #  load_state_dict(assign=True)) and a spread sample of 16 pointers; every 64th step all of them)
         probe = self._ema_probe
-        if probe is not None and probe[0] is encoder_model and all(p.data_ptr() == ptr for p, ptr in probe[1]):
-            return self._ema_table
+        if probe is not None and probe[0] is encoder_model and probe[3] == _PARAM_EPOCH[0]:
+            self._ema_calls = getattr(self, "_ema_calls", 0) + 1
+            check = probe[1] if self._ema_calls % 64 == 0 else probe[2]
+            if all(p.data_ptr() == ptr for p, ptr in check):
+                return self._ema_table
         dst = self.queue_network.vince_parameters()
         src = encoder_model.vince_parameters()
         key = tuple(p.data_ptr() for p in dst) + tuple(p.data_ptr() for p in src)
-        self._ema_probe = (encoder_model, [(p, p.data_ptr()) for p in dst + src])
+        every = [(p, p.data_ptr()) for p in dst + src]
+        step = max(1, len(every) // 16)
+        self._ema_probe = (encoder_model, every, every[::step] + every[-1:], _PARAM_EPOCH[0])
         if self._ema_key != key:
             chunks = []
             for d, s in zip(dst, src):
