@@ -464,7 +464,8 @@ def test_fused_epilogue_routes_equal_separate_bn_apply_bitwise(backbone, B, H):
     for mode, train in (("separate", True), ("fused", True), ("fused_t", True), ("separate", False), ("fused", False)):
         model.load_state_dict(snap)
         model.train(train)
-        runner.two_pass = runner.fold_eval = 0 if mode == "separate" else 1
+        runner.fold_eval = 0 if mode == "separate" else 1
+        runner.two_pass = 0 if mode == "separate" else 2          # 2: every 1x1 expansion takes the two-pass route
         runner.tstats = 1 if mode == "fused_t" else 0
         out = model.get_embeddings({"data": x})
         torch.cuda.synchronize()

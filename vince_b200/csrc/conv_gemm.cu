@@ -143,7 +143,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 // latency-bound with one warp per scheduler (issue slots ~25 % busy, ~1500-2900 cycles per 32-column chunk); with EW = 2
 // the sets work on alternate chunks of a tile, each with its own staging tile, store leader and named barriers.
 template <int BN, int CG, bool HALO, bool RES, int EPI, int EW>
-__global__ void __launch_bounds__(GEMM_THREADS + 128 * (EW - 1), (EW == 1 && EPI != 1) ? 2 : 1)
+// Register budget: 96 per thread unless the apply epilogue (which keeps a chunk of residual in registers) needs more -
+// the small footprint leaves room for two or three streaming (BatchNorm-apply) blocks of the OTHER encoder's stream on
+// the same SM, which is where the two-stream schedule gets its overlap.  (One set: 288 threads, two blocks' worth of
+// registers; two sets: 416 threads launched, bounds declared for 640 so that ptxas caps at 65536 / 640 -> 96.)
+__global__ void __launch_bounds__(EPI == 1 ? GEMM_THREADS + 128 * (EW - 1) : (EW == 1 ? GEMM_THREADS : 640), (EW == 1 && EPI != 1) ? 2 : 1)
 conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
   constexpr int ETHREADS = 128 * EW;               // epilogue threads
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -491,8 +495,8 @@ conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
     const int ltid = etid & 127;                   // thread index inside the set
     const uint32_t bar_a = 2u + 2u * (uint32_t)eset, bar_b = 3u + 2u * (uint32_t)eset;     // the set's named barriers
     const uint32_t staging_s = smem_u32(staging);
-    const int nbuf = p.staging_bufs;               // output staging tiles in total (EW == 2: one per set)
-    const bool one_tile = (EW == 2) || nbuf == 1;  // this set cycles through a single staging tile
+    const int nbuf = p.staging_bufs;               // output staging tiles in total, nbuf / EW per set
+    const bool one_tile = nbuf == EW;              // this set cycles through a single staging tile
     // kernel parameters used per chunk, read once (the asm barriers would otherwise force constant-bank re-reads)
     const bool has_stats = (EPI != 1) && p.stats != nullptr;
     const bool do_store = p.stats_only == 0;
@@ -706,7 +710,9 @@ conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
       for (int chunk = eset; chunk < BN / 32; chunk += EW) {
         const uint32_t chunk_ctr = (uint32_t)local_t * (uint32_t)(BN / 32) + (uint32_t)chunk;   // chunk index in this CTA
         const int c0 = n_blk * BN + chunk * 32;
-        const uint32_t buf = staging_s + (EW == 2 ? (uint32_t)eset : (nbuf == 2 ? (chunk_ctr & 1u) : 0u)) * STAGING_BYTES;
+        // the set's tile(s): tiles [eset * nbuf / EW, ...), alternating with the set's own chunk count when it has two
+        const uint32_t buf = staging_s + ((uint32_t)eset * (uint32_t)(nbuf / EW) +
+                                          (one_tile ? 0u : ((chunk_ctr / (uint32_t)EW) & 1u))) * STAGING_BYTES;
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk * 32, raw);
         tmem_ld_wait();
@@ -997,9 +1003,10 @@ static int num_sms() {
 // bound by its epilogue and shared memory is not needed for a deep operand ring; plus two residual tiles for the apply
 // epilogue with a residual.
 static int staging_tiles(const ConvGemmDesc& d) {
-  int nbuf = (d.K / BK <= 8) ? 2 : 1;
-  const char* e = getenv("VINCE_B200_STAGING");      // debug / A-B comparison: 1 or 2
-  if (e && (atoi(e) == 1 || atoi(e) == 2)) nbuf = atoi(e);
+  // one or two k-blocks per tile: two tiles for each of the two epilogue warp sets (one barrier per chunk)
+  int nbuf = (d.K / BK <= 2 && !d.im2col) ? 4 : ((d.K / BK <= 8) ? 2 : 1);
+  const char* e = getenv("VINCE_B200_STAGING");      // debug / A-B comparison: 1, 2 or 4
+  if (e && (atoi(e) == 1 || atoi(e) == 2 || (atoi(e) == 4 && nbuf == 4))) nbuf = atoi(e);
   return nbuf;
 }
 static size_t staging_bytes(const ConvGemmDesc& d) {
@@ -1321,7 +1328,7 @@ int conv_gemm_launch(const ConvGemmDesc& d_in, cudaStream_t stream) {
   }
   // two epilogue warp sets where the epilogue is the bottleneck: few k-blocks per tile (the layers that already get two
   // staging tiles), never the 3x3 halo path; the transposed statistics pass has no staging at all
-  int ew = ((staging_tiles(d) == 2 || tstats) && kp.a_mode != 2) ? 2 : 1;
+  int ew = ((staging_tiles(d) >= 2 || tstats) && kp.a_mode != 2) ? 2 : 1;
   {
     const char* e = getenv("VINCE_B200_EPI_SETS");     // debug / A-B comparison: 1 forces a single set
     if (e && atoi(e) == 1) ew = 1;

@@ -189,10 +189,10 @@ class EncoderRunner:
         self.block_n_override = None
         import os
         self.halo_mode = int(os.environ.get("VINCE_B200_HALO", "-1"))   # -1 auto, 0 off, 1 force (3x3 stride-1 convs)
-        # train mode: statistics pass + recompute pass for the wide 1x1 expansions (0 = always raw + bn_apply)
-        # (measured on B200, profiles/r02_summary.md: bit-identical results but 5 % slower on ResNet-50 - the expansions
-        #  are bound by the epilogue's shared-memory traffic, not by the HBM write, so it is off by default)
-        self.two_pass = int(os.environ.get("VINCE_B200_TWOPASS", "0"))
+        # train mode: statistics pass + recompute pass for the wide 1x1 expansions (Bottleneck conv3): the raw [M,N] fp32
+        # tensor and the separate BN-apply pass never touch HBM.  0 = never, 1 = where it pays in isolation or relieves HBM
+        # (K <= 128: the 56x56 and 28x28 stages; B200, r02: ResNet-50 step 22.6 -> 21.6 ms), 2 = every expansion.
+        self.two_pass = int(os.environ.get("VINCE_B200_TWOPASS", "1"))
         self.tstats = int(os.environ.get("VINCE_B200_TSTATS", "1"))     # 0: statistics pass in the untransposed form
         # eval mode: BatchNorm(+residual)+ReLU folded into the producing convolution's epilogue (0 = separate bn_apply)
         self.fold_eval = int(os.environ.get("VINCE_B200_FOLD_EVAL", "1"))
@@ -257,7 +257,8 @@ class EncoderRunner:
         recomputing the small-K GEMM is cheaper than writing and re-reading the raw [M,N] tensor."""
         if self.two_pass == 0:
             return False
-        return spec.R == 1 and spec.stride == 1 and spec.Cout >= 4 * spec.K and spec.K <= 512
+        kmax = 128 if self.two_pass == 1 else 512
+        return spec.R == 1 and spec.stride == 1 and spec.Cout >= 4 * spec.K and spec.K <= kmax
 
     def _build_conv_planes(self, arena, act, spec, work, train, launches, relu, res_planes=None, res_side=None):
         """conv + BatchNorm (+ residual) (+ ReLU) -> fp16 planes, through the cheapest available route:
