@@ -186,6 +186,11 @@ int vince_bn_final_pool(const vince_bn_side* main, int32_t res_kind, const void*
  * vince_model.py:144-155 and :164-170. */
 int vince_split_f16(const float* x, void* hi, void* lo, int64_t n, void* stream);
 int vince_round_tf32(const float* x, float* out, int64_t n, void* stream);
+/* debug aid (no reference counterpart): *count += how many of the n fp16 values of an activation / weight plane sit at
+ * the saturation bound +-65504.  The fp32 -> fp16 (hi, lo) split clamps instead of overflowing, so a network whose
+ * activations outgrow fp16's range (large BatchNorm gammas, unnormalised residual sums) clips silently unless checked:
+ * EncoderRunner runs this over every plane it produces when VINCE_B200_CHECK_SATURATION=1. */
+int vince_count_saturated(const void* plane_f16, int64_t n, uint64_t* count, void* stream);
 int vince_l2_normalize(const float* x, float* out, int32_t rows, int32_t D, float eps, void* stream);
 int vince_jigsaw_patchify(const float* x, const int64_t* gather_idx, float* out, int32_t N, int32_t C, int32_t H,
                           int32_t W, void* stream);

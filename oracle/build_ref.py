@@ -3,9 +3,9 @@ TEST / BASELINE INFRASTRUCTURE ONLY - never imported by vince_b200/.
 
     python oracle/build_ref.py        (also called by __graft_entry__.build() when /root/reference is mounted)
 
-The reference is pure Python: "building" it means copying the 11 files its hot path imports
+The reference is pure Python: "building" it means copying the 13 files its hot path imports
 (constants.py, models/{__init__,base_model,vince_model}.py, models/building_blocks/{__init__,backbone_models,resnet}.py,
-utils/{__init__,loss_util,storage_queue,util_functions}.py, plus the four class-name lists util_functions reads at
+utils/{__init__,loss_util,storage_queue,util_functions}.py, solvers/{vince_solver,base_solver}.py, plus the four class-name lists util_functions reads at
 import time; ~140 KB) byte for byte, with their directory layout, into
 oracle/_ref/reference/.  oracle/_ref/ is git-ignored (reference SOURCES never enter the history) but not
 gpurun-ignored, so `bench.py --impl reference` on the GPU box times the reference's own VinceModel / VinceQueueModel /
@@ -26,6 +26,10 @@ FILES = [
     "models/__init__.py", "models/base_model.py", "models/vince_model.py",
     "models/building_blocks/__init__.py", "models/building_blocks/backbone_models.py", "models/building_blocks/resnet.py",
     "utils/__init__.py", "utils/loss_util.py", "utils/storage_queue.py", "utils/util_functions.py",
+    # the training loop itself (tests/test_gpu_parity.py::test_reference_solver_runs_unchanged_on_vince_b200_classes runs
+    # its run_train_iteration, unmodified, against the vince_b200 classes); loaded by file path, so the package
+    # __init__ files of solvers/ and datasets/ (which import every dataset / end-task solver) are not needed
+    "solvers/vince_solver.py", "solvers/base_solver.py",
     # class-name lists utils/util_functions.py:12-33 reads at import time (labels for visualisations; 80 KB)
     "datasets/info_files/imagenet_class_names.json", "datasets/info_files/sun_scene_class_names.txt",
     "datasets/info_files/kinetics_400_class_names.txt", "datasets/info_files/yt8m_class_names.txt",

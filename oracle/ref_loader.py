@@ -72,6 +72,46 @@ def load_reference():
     return ns
 
 
+_solver = None
+
+
+def solver_available():
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "solvers", "vince_solver.py"))
+
+
+def load_reference_solver():
+    """The reference's VinceSolver class (solvers/vince_solver.py, unmodified).  The module is loaded by file path with
+    stub `solvers` / `datasets` packages in sys.modules, so the package __init__ files (which import every dataset and
+    end-task solver, cv2, ...) are never executed; the only name taken from `datasets` is NPZDataset, which
+    run_train_iteration does not touch."""
+    global _solver
+    if _solver is not None:
+        return _solver
+    import importlib.util
+    load_reference()
+    for name in ("solvers", "datasets"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = [os.path.join(REFERENCE_ROOT, name)]
+            sys.modules[name] = m
+    if "datasets.npz_dataset" not in sys.modules:
+        nd = types.ModuleType("datasets.npz_dataset")
+        nd.NPZDataset = object
+        sys.modules["datasets.npz_dataset"] = nd
+    mods = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for name in ("base_solver", "vince_solver"):
+            full = "solvers." + name
+            spec = importlib.util.spec_from_file_location(full, os.path.join(REFERENCE_ROOT, "solvers", name + ".py"))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[full] = mod
+            spec.loader.exec_module(mod)
+            mods[name] = mod
+    _solver = mods["vince_solver"].VinceSolver
+    return _solver
+
+
 def make_args(backbone="ResNet18", num_frames=4, batch_size=8, queue_size=1024, embedding_size=128,
               temperature=0.07, self_temperature=0.03, momentum=0.999, inter_batch_comparison=True,
               self_batch_comparison=False, jigsaw=False):

@@ -75,6 +75,7 @@ SIGNATURES = {
     "vince_bn_final_pool": (c_int32, [POINTER(BnSide), c_int32, c_void_p, c_void_p, POINTER(BnSide), c_void_p,
                                       c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "vince_split_f16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "vince_count_saturated": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
     "vince_round_tf32": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
     "vince_l2_normalize": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),
     "vince_jigsaw_patchify": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),

@@ -135,6 +135,12 @@ int vince_bn_final_pool(const vince_bn_side* main, int32_t res_kind, const void*
                               spatial_nchw, pooled, N, HW, C, S(stream));
 }
 
+int vince_count_saturated(const void* plane, int64_t n, uint64_t* count, void* stream) {
+  VB_REQUIRE(n == 0 || (plane && count), "vince_count_saturated: null pointer");
+  return count_saturated_launch(reinterpret_cast<const __half*>(plane), n, reinterpret_cast<unsigned long long*>(count),
+                                S(stream));
+}
+
 int vince_split_f16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
   VB_REQUIRE(n == 0 || (x && hi), "vince_split_f16: null pointer");
   return split_f16_launch(x, HF(hi), HF(lo), n, S(stream));

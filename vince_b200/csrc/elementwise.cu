@@ -603,6 +603,26 @@ int split_f16_launch(const float* x, __half* hi, __half* lo, int64_t n, cudaStre
   return VB_OK;
 }
 
+// Debug aid: how many values of an fp16 plane sit at the saturation bound +-65504 (the conversions of common.cuh clamp
+// instead of overflowing to inf, so a network whose activations outgrow fp16's range would otherwise clip silently)
+__global__ void count_saturated_kernel(const __half* __restrict__ x, int64_t n, unsigned long long* __restrict__ count) {
+  unsigned int local = 0;
+  const unsigned short* u = reinterpret_cast<const unsigned short*>(x);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    local += ((u[i] & 0x7fffu) >= 0x7bffu) ? 1u : 0u;        // |x| == 65504 (or inf / nan, which must never appear)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local != 0) atomicAdd(count, (unsigned long long)local);
+}
+int count_saturated_launch(const __half* x, int64_t n, unsigned long long* count, cudaStream_t stream) {
+  if (n == 0) return VB_OK;
+  int blocks = div_up(n, 256 * 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  count_saturated_kernel<<<blocks, 256, 0, stream>>>(x, n, count);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB_OK;
+}
+
 // F.normalize(x, dim=1): x / max(||x||_2, eps); one warp per row
 __global__ void l2_normalize_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int D, float eps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

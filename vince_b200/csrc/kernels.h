@@ -104,6 +104,8 @@ int bn_final_pool_launch(const BnSide& main, int res_kind, const __half* res_hi,
                          const BnSide& res_bn, const int64_t* scatter_idx, float* spatial_nchw, float* pooled, int N,
                          int HW, int C, cudaStream_t stream);
 int split_f16_launch(const float* x, __half* hi, __half* lo, int64_t n, cudaStream_t stream);
+// *count += number of plane values at the fp16 saturation bound (debug aid, see vince_count_saturated)
+int count_saturated_launch(const __half* x, int64_t n, unsigned long long* count, cudaStream_t stream);
 int l2_normalize_launch(const float* x, float* out, int rows, int D, float eps, cudaStream_t stream);
 // NCHW fp32 [N,C,H,W] -> jigsaw patches NCHW [9N,C,H3,W3] (pad bottom/right with zeros to a multiple of 3)
 int jigsaw_patchify_launch(const float* x, const int64_t* gather_idx, float* out, int N, int C, int H, int W, int H3,

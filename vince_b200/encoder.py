@@ -147,7 +147,7 @@ class Act:
 
 
 class _Plan:
-    __slots__ = ("launches", "replay", "stats", "idx_gather", "idx_scatter", "x_hi", "x_lo", "final", "out_shape", "arena_bytes",
+    __slots__ = ("launches", "replay", "sat_counter", "stats", "idx_gather", "idx_scatter", "x_hi", "x_lo", "final", "out_shape", "arena_bytes",
                  "n_static", "tape", "shape", "last_input", "last_gather")
 
 
@@ -194,6 +194,11 @@ class EncoderRunner:
         # (K <= 128: the 56x56 and 28x28 stages; B200, r02: ResNet-50 step 22.6 -> 21.6 ms), 2 = every expansion.
         self.two_pass = int(os.environ.get("VINCE_B200_TWOPASS", "1"))
         self.tstats = int(os.environ.get("VINCE_B200_TSTATS", "1"))     # 0: statistics pass in the untransposed form
+        # debug aid: count the activation values that hit the fp16 saturation bound (+-65504) in every plane a forward
+        # produces and warn when there are any - the (hi, lo) split clamps instead of overflowing, so a network whose
+        # activations outgrow fp16's range would otherwise clip silently.  Costs one small launch per plane pair.
+        self.check_saturation = int(os.environ.get("VINCE_B200_CHECK_SATURATION", "0"))
+        self.saturated = 0          # values at the bound seen by the last checked forward
         # eval mode: BatchNorm(+residual)+ReLU folded into the producing convolution's epilogue (0 = separate bn_apply)
         self.fold_eval = int(os.environ.get("VINCE_B200_FOLD_EVAL", "1"))
 
@@ -204,6 +209,7 @@ class EncoderRunner:
         new = EncoderRunner(copy.deepcopy(self.model, memo), self.passes)
         new.block_n_override = self.block_n_override
         new.two_pass, new.fold_eval, new.tstats = self.two_pass, self.fold_eval, self.tstats
+        new.check_saturation = self.check_saturation
         new.input_mean, new.input_std = self.input_mean, self.input_std
         return new
 
@@ -284,6 +290,7 @@ class EncoderRunner:
             arena.free(raw)
             out = Act(hi, lo, act.N, P, Q, C)
             self._last_unit["out"] = out
+            self._sat(launches, out)
             return out, P, Q
         if train:
             # statistics pass: transposed form (channels on the accumulator rows) for plain GEMMs
@@ -301,7 +308,12 @@ class EncoderRunner:
         out = Act(hi, lo, act.N, P, Q, C)
         # (no raw tensor on this route: such plans are never taped - forward() disables the two-pass route when taping)
         self._last_unit = dict(spec=spec, x=act, raw=None, coef=self._coef(spec, work), P=P, Q=Q, M=M, out=out)
+        self._sat(launches, out)
         return out, P, Q
+
+    def _sat(self, launches, act):
+        if self.check_saturation:
+            launches.append(ops.build_count_saturated(act.hi, self._sat_counter))
 
     def _planes(self, arena, M, C):
         hi = arena.alloc((M, C), torch.float16)
@@ -322,6 +334,7 @@ class EncoderRunner:
         # BN work buffer (sums, coefficients, finalize counters); zeroed once per train-mode forward
         stats = work = torch.zeros((self.stats_total,), device=dev, dtype=torch.float64)
         plan.stats = work
+        self._sat_counter = plan.sat_counter = torch.zeros((1,), device=dev, dtype=torch.int64)
         if not train:
             # eval-mode BatchNorm: coefficients from the running statistics, one tiny launch per BN layer
             for spec in self.bank.specs:
@@ -346,6 +359,7 @@ class EncoderRunner:
         launches.append(ops.build_bn_relu_maxpool(self._side(raw, self.stem, stats), hi, lo, N, P, Q, 64))
         arena.free(raw)
         act = Act(hi, lo, N, P2, Q2, 64)
+        self._sat(launches, act)
         # ---- residual blocks ----
         for bi, blk in enumerate(self.blocks):
             last = bi == len(self.blocks) - 1
@@ -396,7 +410,11 @@ class EncoderRunner:
             arena.free(raw_ds, act.hi, act.lo)
             act = nxt
         plan.launches = launches
-        plan.replay = ops.GraphReplay(launches, pre=stats.zero_ if train else None)
+        pre = stats.zero_ if train else None
+        if self.check_saturation:
+            counter = plan.sat_counter
+            pre = (lambda: (stats.zero_(), counter.zero_())) if train else counter.zero_
+        plan.replay = ops.GraphReplay(launches, pre=pre)
         plan.arena_bytes = arena.total
         plan.n_static = len(launches)
         plan.tape = dict(stem=tape_stem, blocks=tape_blocks, pool_out=tape_blocks[0]["input"]) if tape else None
@@ -436,7 +454,8 @@ class EncoderRunner:
             self.bank.refresh()
             tape = bool(tape and train)
             two_pass = 0 if tape else self.two_pass        # the backward reads the raw tensors: no recompute route
-            key = (N, H, W, bool(train), two_pass, self.tstats, self.fold_eval, tape, dev.index, self.bank.generation)
+            key = (N, H, W, bool(train), two_pass, self.tstats, self.fold_eval, tape, self.check_saturation, dev.index,
+                   self.bank.generation)
             if self._plans and next(iter(self._plans))[-1] != self.bank.generation:
                 self._plans.clear()                         # parameters moved: every cached pointer is stale
             plan = self._plans.get(key)
@@ -466,6 +485,13 @@ class EncoderRunner:
             pooled = torch.empty((N, f["C"]), device=dev, dtype=torch.float32)
             ops.build_bn_final_pool(f["main"], f["N"], f["HW"], f["C"], spatial, pooled, scatter_idx=si, **f["kw"])()
             self.launches = plan.n_static + 3 + (1 if train else 0)       # + weight_prep, stem_pack, final (+ memset)
+            if self.check_saturation:
+                self.saturated = int(plan.sat_counter.item())           # (debug mode: one synchronisation per forward)
+                if self.saturated:
+                    import warnings
+                    warnings.warn("vince_b200: %d activation values reached the fp16 saturation bound (+-65504) in this "
+                                  "forward and were clamped; the fp16x3 arithmetic is not fp32-grade for this network / "
+                                  "input (see DESIGN.md, numerical strategy)" % self.saturated)
             if tape:
                 plan.last_input, plan.last_gather = x, gi
                 self.tape = plan

@@ -204,6 +204,12 @@ def build_conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, bl
     ref = ctypes.byref(d)
     # algorithmic FLOPs: the statistics pass of the two-pass scheme is recomputation - it gets no credit
     flops = 0.0 if stats_only else 2.0 * M * N * (geom.get("K_true", K) if geom is not None else K)
+    # ... and the algorithmic HBM bytes of the launch (activations once, at fp32 width = the two fp16 planes; weights;
+    # output; residual) for the launches whose role is the streaming one: statistics pass and apply epilogue
+    kind = "stats" if stats_only else ("apply" if out_planes is not None else "gemm")
+    in_bytes = 4.0 * (M * K if geom is None else geom["batch"] * geom["H"] * geom["W"] * geom["Cin"])
+    nbytes = in_bytes + 4.0 * N * K + (0.0 if stats_only else 4.0 * M * N) + \
+        (4.0 * M * N if (res_planes is not None or res_raw is not None) else 0.0)
     check = _lib.check
 
     def run():
@@ -214,7 +220,7 @@ def build_conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, bl
             e0.record()
             check(fn(ref, stream), "vince_conv_fwd")
             e1.record()
-            PROFILE.append(("conv_gemm", flops, e0, e1))
+            PROFILE.append((kind, flops, nbytes, e0, e1))
         else:
             check(fn(ref, stream), "vince_conv_fwd")
     run._keep = (d, a_hi, a_lo, w_hi, w_lo, out, scale, bias, stats, bn, coef, counter, out_planes, ep_coef, res_planes,
@@ -224,6 +230,14 @@ def build_conv_fwd(a_hi, a_lo, w_hi, w_lo, out, M, N, K, passes=3, geom=None, bl
 
 def conv_fwd(*a, **k):
     build_conv_fwd(*a, **k)()
+
+
+def build_count_saturated(plane, counter):
+    """counter (int64 [1], device) += number of values of the fp16 `plane` at the saturation bound +-65504 (debug aid)."""
+    run = _bind(_lib.lib().vince_count_saturated, "vince_count_saturated", _ptr(plane, torch.float16, "plane"),
+                plane.numel(), _ptr(counter, torch.int64, "counter"))
+    run._keep = (plane, counter)
+    return run
 
 
 def stem_geometry(H, W):
