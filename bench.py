@@ -422,7 +422,7 @@ def run_ours(a):
     if not wl["jigsaw"] and not a.no_train:
         try:
             t_steps = max(3, min(a.steps, 10))
-            for _ in range(2):
+            for _ in range(4):          # (tape plan + backward list are built, run eagerly once, then captured as graphs)
                 hp.step(data, queue_data, train=True)
             t_ms = timed(lambda: hp.step(data, queue_data, train=True), t_steps)
             train = {"ms_per_step": round(t_ms / t_steps, 4), "value": round(frames_per_step * t_steps / (t_ms / 1e3), 1),
@@ -466,12 +466,12 @@ def run_ours(a):
     iso_tf = iso_conv_flops / (iso_conv_ms / 1e3) / 1e12 if iso_conv_ms > 0 else 0.0
     step_flops = conv_flops / max(a.steps, 1)
     streaming = {}
-    for kind, what in (("apply", "recompute pass of the two-pass BatchNorm route: GEMM + BatchNorm scale/shift + residual + "
+    for rkind, what in (("apply", "recompute pass of the two-pass BatchNorm route: GEMM + BatchNorm scale/shift + residual + "
                                  "ReLU -> fp16 planes in the epilogue (Bottleneck 1x1 expansions with K <= 128)"),
                        ("stats", "transposed statistics pass of the same route (nothing stored)")):
-        f_, b_, t_, n_ = role(kind)
+        f_, b_, t_, n_ = role(rkind)
         if n_:
-            streaming[kind] = {"bound": "hbm", "launches_timed": n_, "avg_launch_us": round(t_ * 1e3 / n_, 2),
+            streaming[rkind] = {"bound": "hbm", "launches_timed": n_, "avg_launch_us": round(t_ * 1e3 / n_, 2),
                                "algorithmic_mbytes_per_launch": round(b_ / n_ / 1e6, 1),
                                "achieved": round(b_ / (t_ / 1e3) / 1e9, 1), "peak": peaks["hbm"], "unit": "GB/s",
                                "frac": round(b_ / (t_ / 1e3) / 1e9 / peaks["hbm"], 4),

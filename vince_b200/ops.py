@@ -50,20 +50,30 @@ class GraphReplay:
             return self._eager()
         cur = torch.cuda.current_stream()
         g = torch.cuda.CUDAGraph()
-        try:
-            # capture on a side stream that first waits for the caller's stream (torch.cuda.graph does both), then replay
-            # on the caller's stream: capture itself executes nothing
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                self._eager()
-        except Exception:
+        # capture on a side stream ordered after the caller's stream; capture executes nothing.  (Not the
+        # `with torch.cuda.graph(...)` helper: it synchronises the device and empties the caching allocator first, which
+        # cost a ResNet-50 training step hundreds of milliseconds of re-allocation when a capture fell into a timed region.)
+        side = torch.cuda.Stream(device=cur.device)
+        side.wait_stream(cur)
+        ok = True
+        with torch.cuda.stream(side):
+            try:
+                g.capture_begin(capture_error_mode="thread_local")
+                try:
+                    self._eager()
+                finally:
+                    g.capture_end()
+            except Exception:
+                ok = False
+        cur.wait_stream(side)
+        if not ok:
             GraphReplay.enabled = False      # e.g. a driver without the needed capture support: stay eager, loudly once
             import warnings
             warnings.warn("vince_b200: CUDA graph capture failed, replaying launch lists eagerly")
             torch.cuda.synchronize()
             return self._eager()
         self.graph = g
-        with torch.cuda.stream(cur):
-            g.replay()
+        g.replay()
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
