@@ -18,6 +18,7 @@
 // epilogue threads, in place in shared memory, right after their TMA tiles land (no pre-pass, no rounded copies in
 // HBM); positives use the un-rounded data.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -49,6 +50,7 @@ struct NceParams {
   float* neg_max;
   float* row_lse;
   float* scalars;
+  int debug;                       // timing experiments only (VINCE_B200_NCE_DEBUG bits): results are garbage
 };
 
 __device__ __forceinline__ uint32_t rna_tf32(uint32_t v) {
@@ -205,6 +207,35 @@ __global__ void __launch_bounds__(NCE_THREADS, 1) infonce_main_kernel(const __gr
       fence_proxy_async_smem();
       mbar_arrive(q_ready);
     }
+    // positives: q_i . k_j in exact fp32 (vince_model.py:213-233 computes them in fp32).  The rows of this query block are
+    // dealt out over its `slices` CTAs (one or two rows each), and a row is one warp's work: the 32 lanes split the D
+    // elements (coalesced 128-byte reads), lane 0 stores the result straight into the pos_sim output, which the block's
+    // last CTA reads back in the tail.  Runs under the TMA prologue; doing all 128 rows in the tail instead cost the last
+    // CTA ~60 us of serial L2 round trips (ncu: SMs active 27k of 157k elapsed cycles).
+    {
+      int idx = 0;
+      for (int rr = (p.debug & 4) ? NCE_BM : sidx; rr < NCE_BM; rr += p.slices, ++idx) {
+        const int ri = m_blk * NCE_BM + rr;
+        if ((idx & 3) != quarter || ri >= p.B) continue;          // warp-uniform
+        const int pos0 = p.nf > 0 ? (ri / p.nf) * p.nf : ri;
+        const float* qr = p.q + (size_t)ri * p.D;
+        float qv[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) qv[t] = (lane + 32 * t < p.D) ? __ldg(qr + lane + 32 * t) : 0.f;
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+          if (pp < p.nP) {
+            const float* kr = p.keys + (size_t)(pos0 + pp) * p.D;
+            float d = 0.f;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) d = fmaf(qv[t], (lane + 32 * t < p.D) ? __ldg(kr + lane + 32 * t) : 0.f, d);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            if (lane == 0) p.pos_sim[(size_t)ri * p.nP + pp] = d;
+          }
+        }
+      }
+    }
     for (int t = t_begin, lt = 0; t < t_end; ++t, ++lt) {
       const int acc = lt & 1;
       const uint32_t acc_phase = (lt >> 1) & 1;
@@ -262,44 +293,52 @@ __global__ void __launch_bounds__(NCE_THREADS, 1) infonce_main_kernel(const __gr
     p.partials[((size_t)m_blk * p.slices + sidx) * NCE_BM + r] = make_float2(nmax, Z);
 
     // ---------------- fused tail: last CTA of this query block finalizes its 128 rows ----------------
+    if (p.debug & 8) goto tail_done;
     __threadfence();
     named_bar_sync(1, 128);
     if (etid == 0) flags[0] = (atomicAdd(&p.counters[m_blk], 1u) == (unsigned)p.slices - 1u) ? 1u : 0u;
     named_bar_sync(1, 128);
     if (flags[0]) {
       __threadfence();
-      if (i < p.B) {
+      if (i < p.B && !(p.debug & 1)) {
+        // merge the per-CTA partials of this row (coalesced across the block's threads; unrolled so that several of the
+        // L2 round trips are in flight at once)
         const float2* part = p.partials + (size_t)m_blk * p.slices * NCE_BM + r;
-        float gmax = -INFINITY;
-        for (int s_ = 0; s_ < p.slices; ++s_) gmax = fmaxf(gmax, __ldcg(&part[(size_t)s_ * NCE_BM]).x);
-        float Zs = 0.f;
-        for (int s_ = 0; s_ < p.slices; ++s_) {
-          const float2 pr = __ldcg(&part[(size_t)s_ * NCE_BM]);
-          if (pr.x != -INFINITY) Zs += pr.y * exp2f((pr.x - gmax) * c);
-        }
-        // positives: exact fp32 dot products (vince_model.py:213-233 computes them in fp32)
-        const int pos0 = p.nf > 0 ? (i / p.nf) * p.nf : i;
-        float zmax = (gmax == -INFINITY) ? -INFINITY : gmax / p.temperature;
-        float sig[8];
-        const float4* qr = reinterpret_cast<const float4*>(p.q + (size_t)i * p.D);
-        for (int pp = 0; pp < p.nP; ++pp) {
-          const float4* kr = reinterpret_cast<const float4*>(p.keys + (size_t)(pos0 + pp) * p.D);
-          float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-          for (int e = 0; e < p.D / 4; ++e) {
-            const float4 a = __ldg(&qr[e]), b = __ldg(&kr[e]);
-            d0 = fmaf(a.x, b.x, d0), d1 = fmaf(a.y, b.y, d1), d2 = fmaf(a.z, b.z, d2), d3 = fmaf(a.w, b.w, d3);
+        // one pass, 16 partials at a time held in registers so that 16 L2 round trips are in flight together (a plain
+        // loop, even unrolled, issued them one after another: 31 us for the 2 x 74 loads of a row)
+        float gmax = -INFINITY, Zs = 0.f;
+        for (int s0 = 0; s0 < p.slices; s0 += 16) {
+          float2 v[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u)
+            v[u] = (s0 + u < p.slices) ? __ldcg(&part[(size_t)(s0 + u) * NCE_BM]) : make_float2(-INFINITY, 0.f);
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            if (v[u].x != -INFINITY) {
+              const float mn = fmaxf(gmax, v[u].x);
+              Zs = Zs * exp2f((gmax - mn) * c) + v[u].y * exp2f((v[u].x - mn) * c);     // gmax = -inf: Zs is 0, exp2(-inf) = 0
+              gmax = mn;
+            }
           }
-          sig[pp] = (d0 + d1) + (d2 + d3);
-          zmax = fmaxf(zmax, sig[pp] / p.temperature);
         }
+        // positives: computed (exact fp32) at the start of the kernel by the CTAs of this block, see above
+        float sig[8];
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) sig[pp] = (pp < p.nP) ? __ldcg(&p.pos_sim[(size_t)i * p.nP + pp]) : 0.f;
+        float zmax = (gmax == -INFINITY) ? -INFINITY : gmax / p.temperature;
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp)
+          if (pp < p.nP) zmax = fmaxf(zmax, sig[pp] / p.temperature);
         // Zneg relative to the row max over ALL columns (loss_util.py:24)
         const float Zn = (gmax == -INFINITY) ? 0.f : Zs * expf(gmax / p.temperature - zmax);
-        for (int pp = 0; pp < p.nP; ++pp) {
-          const float sp = sig[pp] / p.temperature - zmax;
-          const float logsm = sp - logf(expf(sp) + Zn);
-          p.dists[(size_t)i * p.nP + pp] = -logsm;
-          p.weights[(size_t)i * p.nP + pp] = expf(logsm);
-          p.pos_sim[(size_t)i * p.nP + pp] = sig[pp];
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+          if (pp < p.nP) {
+            const float sp = sig[pp] / p.temperature - zmax;
+            const float logsm = sp - logf(expf(sp) + Zn);
+            p.dists[(size_t)i * p.nP + pp] = -logsm;
+            p.weights[(size_t)i * p.nP + pp] = expf(logsm);
+          }
         }
         p.neg_max[i] = gmax;
         p.row_lse[2 * i] = zmax;
@@ -310,7 +349,7 @@ __global__ void __launch_bounds__(NCE_THREADS, 1) infonce_main_kernel(const __gr
       named_bar_sync(1, 128);
       if (etid == 0) flags[1] = (atomicAdd(&p.counters[p.nmb], 1u) == (unsigned)p.nmb - 1u) ? 1u : 0u;
       named_bar_sync(1, 128);
-      if (flags[1]) {
+      if (flags[1] && !(p.debug & 2)) {
         __threadfence();
         float a[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
         for (int row = etid; row < p.B; row += 128) {
@@ -338,6 +377,7 @@ __global__ void __launch_bounds__(NCE_THREADS, 1) infonce_main_kernel(const __gr
         }
       }
     }
+  tail_done:;
   }
 
   tc_fence_before_sync();
@@ -491,6 +531,7 @@ int infonce_fwd_launch(const InfoNceDesc& d, cudaStream_t stream) {
   kp.temperature = d.temperature;
   kp.dists = d.dists, kp.weights = d.weights, kp.pos_sim = d.pos_sim, kp.neg_max = d.neg_max, kp.row_lse = d.row_lse;
   kp.scalars = d.scalars;
+  kp.debug = getenv("VINCE_B200_NCE_DEBUG") ? atoi(getenv("VINCE_B200_NCE_DEBUG")) : 0;
 
   if (T > 0) {
     rc = encode_tma_2d(&kp.q_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.q, d.D, d.B, (uint64_t)d.D * 4, 32, NCE_BM,
