@@ -449,7 +449,8 @@ def test_encoder_full_size_train_mode_vs_oracle(backbone):
     assert torch.equal(outs[0], outs[1])
 
 
-@pytest.mark.parametrize("backbone,B,H", [("ResNet50", 16, 96), ("ResNet18", 16, 64), ("ResNet50", 64, 224)])
+@pytest.mark.parametrize("backbone,B,H", [("ResNet50", 16, 96), ("ResNet18", 16, 64), ("ResNet50", 64, 224),
+                                          ("ResNet50", 3, 72)])      # last: ragged tiles (972 / 243 / 75 / 27 rows)
 def test_fused_epilogue_routes_equal_separate_bn_apply_bitwise(backbone, B, H):
     """The apply epilogue (BatchNorm scale/shift + residual + ReLU -> fp16 planes inside the convolution) performs the
     same fp32 operations in the same order as vince_bn_apply on the same accumulators, so (1) the train-mode

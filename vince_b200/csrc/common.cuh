@@ -100,6 +100,15 @@ __device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
 __device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void* gptr) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
 }
+// same, asking L2 to fetch the surrounding 256 bytes (the neighbouring channel chunks of the row are wanted next)
+__device__ __forceinline__ void cp_async_16_l2_256(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+// this thread's arrival on `bar` is deferred until all of its prior cp.async copies have landed (the barrier's arrival
+// count must include it: .noinc)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 

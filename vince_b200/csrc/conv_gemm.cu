@@ -41,6 +41,8 @@ constexpr size_t SMEM_BUDGET = 226 * 1024;    // of 227 KB: leaves the 1 KB syst
 struct GemmKernelParams {
   CUtensorMap a_hi, a_lo, b_hi, b_lo, out;
   CUtensorMap out_hi, out_lo;    // EPI == 1: fp16 (hi, lo) output planes (box 32 channels x 128 rows, SWIZZLE_64B)
+  int res_fetch;                 // EPI == 1: residual tiles are fetched by two extra warps (cp.async) into a ring of
+  int res_slots;                 // res_slots 16 KB tiles behind the output staging tiles (0: row owners load registers)
   int staging_bufs;              // output staging tiles in shared memory (1 or 2)
   uint32_t staging_total;        // bytes of the staging area: staging_bufs output tiles (+ 2 residual tiles, EPI == 1)
   // EPI == 1 ("apply" epilogue): out = relu?( acc*alpha*coef[c] + coef[N+c] + residual ) split into fp16 planes
@@ -147,7 +149,7 @@ template <int BN, int CG, bool HALO, bool RES, int EPI, int EW>
 // the small footprint leaves room for two or three streaming (BatchNorm-apply) blocks of the OTHER encoder's stream on
 // the same SM, which is where the two-stream schedule gets its overlap.  (One set: 288 threads, two blocks' worth of
 // registers; two sets: 416 threads launched, bounds declared for 640 so that ptxas caps at 65536 / 640 -> 96.)
-__global__ void __launch_bounds__(EPI == 1 ? GEMM_THREADS + 128 * (EW - 1) : (EW == 1 ? GEMM_THREADS : 640), (EW == 1 && EPI != 1) ? 2 : 1)
+__global__ void __launch_bounds__(EPI == 1 ? GEMM_THREADS + 128 * (EW - 1) + 64 : (EW == 1 ? GEMM_THREADS : 640), (EW == 1 && EPI != 1) ? 2 : 1)
 conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
   constexpr int ETHREADS = 128 * EW;               // epilogue threads
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -174,7 +176,9 @@ conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
   uint64_t* b_empty = b_full + MAX_RING;
   uint64_t* tmem_full = b_empty + MAX_RING;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_full = tmem_empty + 2;             // [4] residual ring (EPI == 1 with fetcher warps)
+  uint64_t* res_empty = res_full + 4;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_empty + 4);
   uint32_t* last_flag = tmem_ptr + 1;
   double* smem_stats = reinterpret_cast<double*>(tmem_ptr + 2);     // [4 epilogue warps][2][BN], warp-private
 
@@ -203,6 +207,10 @@ conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
     for (int s = 0; s < (RES ? 1 : p.b_stages); ++s) {       // RES: one barrier for the one-time weight load
       mbar_init(&b_full[s], (uint32_t)planes * (merged ? 2u : 1u) + fwd);
       mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&res_full[s], 64);                 // every fetcher thread arrives once its copies have landed
+      mbar_init(&res_empty[s], 128);               // every thread of the consuming epilogue set
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -480,6 +488,56 @@ conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
         }
       }
     }
+  } else if (EPI == 1 && warp >= EPI_WARP0 + 4 * EW) {
+    // ======================= residual fetchers (two warps; launched only when p.res_fetch) =======================
+    // The residual tile of chunk k of this CTA (32 channels x 128 rows: 8 KB hi + 8 KB lo planes, or 16 KB of the raw fp32
+    // tensor) is copied with cp.async (LSU path: it does not queue behind the TMA output stores) into slot k % res_slots of
+    // a ring behind the staging tiles, in the swizzled layout the row owners read conflict-free; the copies of a slot are
+    // tracked by its mbarrier (cp.async.mbarrier.arrive), so the fetchers run res_slots chunks ahead of the epilogue and
+    // neither the row owners nor their proxy fence ever wait on a global load.
+    const int f = threadIdx.x - (EPI_WARP0 + 4 * EW) * 32;          // 0..63
+    const int R = p.res_slots;
+    const uint32_t ring_s = smem_u32(staging) + (uint32_t)p.staging_bufs * STAGING_BYTES;
+    const int res_kind = p.res_kind;
+    const long long Mrows = p.M;
+    const int N = p.N;
+    uint32_t k = 0;
+    for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
+      const int tb = tile % p.tiles_per_batch;
+      const int m_blk = (tb % p.num_m_blocks) * CG + (int)cta_rank;
+      const int n_blk = tb / p.num_m_blocks;
+      const long long m0 = (long long)m_blk * BM;
+      int nvalid = BM;
+      if (m0 + nvalid > Mrows) nvalid = (int)(Mrows - m0 > 0 ? Mrows - m0 : 0);
+      for (int chunk = 0; chunk < BN / 32; ++chunk, ++k) {
+        const uint32_t slot = k % (uint32_t)R;
+        mbar_wait(&res_empty[slot], ((k / (uint32_t)R) & 1u) ^ 1u);
+        const uint32_t dst = ring_s + slot * STAGING_BYTES;
+        const int c0 = n_blk * BN + chunk * 32;
+        if (res_kind == 1) {
+#pragma unroll 4
+          for (int it = 0; it < 16; ++it) {
+            const int idx = it * 64 + f;                 // 512 hi pieces then 512 lo pieces of 16 bytes
+            const int plane = idx >> 9, rem = idx & 511;
+            const int r = rem >> 2, j = rem & 3;
+            const __half* src = plane == 0 ? p.res_hi : p.res_lo;
+            if (r < nvalid && src != nullptr)
+              cp_async_16_l2_256(dst + (uint32_t)plane * 8192u + (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)),
+                                 src + (m0 + r) * N + c0 + j * 8);
+          }
+        } else {
+#pragma unroll 4
+          for (int it = 0; it < 16; ++it) {
+            const int idx = it * 64 + f;                 // 1024 pieces of 16 bytes: 8 per 128-byte row
+            const int r = idx >> 3, j = idx & 7;
+            if (r < nvalid)
+              cp_async_16_l2_256(dst + (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)), p.res_raw + (m0 + r) * N + c0 + j * 4);
+          }
+        }
+        cp_async_mbar_arrive_noinc(&res_full[slot]);
+      }
+    }
+    cp_async_wait_all();
   } else {
     // ======================= epilogue (warps 5..8) =======================
     // Per 32-column chunk: TMEM -> registers (one accumulator row per thread) -> epilogue math -> swizzled staging
@@ -571,7 +629,9 @@ conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
         for (int j = 0; j < 4; ++j) ldg256_stream(p.res_raw + e + 8 * j, &rres[8 * j]);
       }
     };
-    if (EPI == 1) load_residual(tile_start, eset);
+    const bool res_fetch = (EPI == 1) && p.res_fetch != 0 && res_kind != 0;
+    const uint32_t ring_s = staging_s + (uint32_t)nbuf * STAGING_BYTES;
+    if (EPI == 1 && !res_fetch) load_residual(tile_start, eset);
     if (EPI == 2) {
       // ---- transposed statistics pass: this thread owns channel (m_blk * 128 + row) of every tile it sees ----
       const int NC = p.stat_channels;
@@ -645,7 +705,7 @@ conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
         srow = hy * p.W + hx;
       }
       valid = valid && srow < nvalid;
-      if (EPI == 1 && res_kind != 0 && tile + tile_step < num_tiles) {
+      if (EPI == 1 && res_kind != 0 && !res_fetch && tile + tile_step < num_tiles) {
         // the residual rows of this CTA's NEXT tile: ask L2 for them now, a whole tile time before the 256-bit loads
         // above want them (those are issued only one chunk ahead, less than a DRAM round trip under load)
         long long m0n;
@@ -728,6 +788,41 @@ conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
           }
         }
         if (EPI == 1) {
+          // fetcher mode: the residual tile of this chunk sits in ring slot chunk_ctr % res_slots once its barrier flips;
+          // this row's 32 channels are copied to registers (same conflict-free swizzle as the staging tiles)
+          if (res_fetch) {
+            const uint32_t slot = chunk_ctr % (uint32_t)p.res_slots;
+            mbar_wait(&res_full[slot], (chunk_ctr / (uint32_t)p.res_slots) & 1u);
+            const uint32_t rt = ring_s + slot * STAGING_BYTES;
+            if (res_kind == 1) {
+              const uint32_t rsw = (uint32_t)((srow >> 1) & 3);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 fh = lds_v4(rt + (uint32_t)(srow * 64 + ((j ^ rsw) << 4)));
+                const float4 fl = lds_v4(rt + 8192u + (uint32_t)(srow * 64 + ((j ^ rsw) << 4)));
+                rres[4 * j + 0] = __float_as_uint(fh.x), rres[4 * j + 1] = __float_as_uint(fh.y);
+                rres[4 * j + 2] = __float_as_uint(fh.z), rres[4 * j + 3] = __float_as_uint(fh.w);
+                rres[16 + 4 * j + 0] = __float_as_uint(fl.x), rres[16 + 4 * j + 1] = __float_as_uint(fl.y);
+                rres[16 + 4 * j + 2] = __float_as_uint(fl.z), rres[16 + 4 * j + 3] = __float_as_uint(fl.w);
+              }
+              if (p.res_lo == nullptr) {
+#pragma unroll
+                for (int j = 16; j < 32; ++j) rres[j] = 0u;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 fr = lds_v4(rt + (uint32_t)(srow * 128 + ((j ^ (srow & 7)) << 4)));
+                rres[4 * j + 0] = __float_as_uint(fr.x), rres[4 * j + 1] = __float_as_uint(fr.y);
+                rres[4 * j + 2] = __float_as_uint(fr.z), rres[4 * j + 3] = __float_as_uint(fr.w);
+              }
+            }
+            if (!valid) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) rres[j] = 0u;
+            }
+            mbar_arrive(&res_empty[slot]);              // the slot may be refilled (this thread holds its row in registers)
+          }
           // with one output staging tile everybody must be done with the previous chunk's tile before it is overwritten
           if (one_tile) {
             if (store_leader && store_pending) tma_store_wait_read0();
@@ -795,7 +890,7 @@ conv_gemm_kernel(const __grid_constant__ GemmKernelParams p) {
           // this chunk's residual is consumed: fetch the one of this set's next chunk (same tile, or the next tile's first).
           // (Issued here, before the proxy fence, the fence absorbs part of the load latency - ncu: 25 % of the epilogue's
           //  samples on fence + barrier - but issuing after the barrier was measured slower still: 497 vs 434 us.)
-          if (res_kind != 0) {
+          if (res_kind != 0 && !res_fetch) {
             if (chunk + EW < CHUNKS) load_residual(tile, chunk + EW);
             else load_residual(tile + tile_step, eset);
           }
@@ -1002,26 +1097,38 @@ static int num_sms() {
 // Output staging tiles: two (one barrier per chunk instead of two) when a tile has few k-blocks, i.e. when the layer is
 // bound by its epilogue and shared memory is not needed for a deep operand ring; plus two residual tiles for the apply
 // epilogue with a residual.
+// Apply epilogue with a residual on the small-K plain GEMMs (the two-pass route's recompute pass): the residual tiles are
+// fetched by two extra warps into a shared-memory ring (see the kernel); needs the two epilogue sets' configuration
+static bool use_res_fetch(const ConvGemmDesc& d) {
+  if (!(d.out_hi != nullptr && d.res_kind != 0 && !d.im2col && d.kchunk == 0 && d.K / BK <= 8)) return false;
+  const char* e = getenv("VINCE_B200_RES_FETCH");    // debug / A-B comparison: 0 = row owners load the residual themselves
+  if (e && atoi(e) == 0) return false;
+  e = getenv("VINCE_B200_EPI_SETS");
+  if (e && atoi(e) == 1) return false;
+  return true;
+}
 static int staging_tiles(const ConvGemmDesc& d) {
   // one or two k-blocks per tile: two tiles for each of the two epilogue warp sets (one barrier per chunk)
   int nbuf = (d.K / BK <= 2 && !d.im2col) ? 4 : ((d.K / BK <= 8) ? 2 : 1);
+  if (d.res_slots > 0) nbuf = 2;                     // the residual ring takes the room of the second pair of tiles
   const char* e = getenv("VINCE_B200_STAGING");      // debug / A-B comparison: 1, 2 or 4
   if (e && (atoi(e) == 1 || atoi(e) == 2 || (atoi(e) == 4 && nbuf == 4))) nbuf = atoi(e);
   return nbuf;
 }
 static size_t staging_bytes(const ConvGemmDesc& d) {
   if (d.stats_only == 2) return 0;                   // transposed statistics pass: nothing is staged
-  return (size_t)STAGING_BYTES * staging_tiles(d);
+  return (size_t)STAGING_BYTES * (staging_tiles(d) + d.res_slots);
 }
 static size_t fixed_smem(int bn, const ConvGemmDesc& d) {
   // alignment slack + staging + barriers + flags + per-channel area (EPI 0: [4 warps][2][bn] double-float sums,
   // EPI 1: 4 x bn coefficients, EPI 2: unused)
   const size_t chan = d.out_hi != nullptr ? (size_t)4 * bn * 4 + 16 : (d.stats_only == 2 ? 16 : (size_t)8 * bn * 8);
-  return 1024 + staging_bytes(d) + (4 * MAX_RING + 4) * 8 + 32 + chan;
+  return 1024 + staging_bytes(d) + (4 * MAX_RING + 12) * 8 + 32 + chan;
 }
 
 template <int BN, int CG, bool HALO, bool RES, int EPI, int EW = 1>
 static int launch_gemm(const GemmKernelParams& kp, size_t smem, int grid, cudaStream_t stream) {
+  const int fetch_threads = (EPI == 1 && kp.res_fetch) ? 64 : 0;       // two residual fetcher warps
   static bool smem_set[MAX_DEVICES] = {false};       // per instantiation AND device (the attribute is per context)
   const int dev = current_device();
   constexpr int THREADS = GEMM_THREADS + 128 * (EW - 1);
@@ -1031,13 +1138,13 @@ static int launch_gemm(const GemmKernelParams& kp, size_t smem, int grid, cudaSt
     smem_set[dev] = true;
   }
   if (CG == 1) {
-    conv_gemm_kernel<BN, CG, HALO, RES, EPI, EW><<<grid, THREADS, smem, stream>>>(kp);
+    conv_gemm_kernel<BN, CG, HALO, RES, EPI, EW><<<grid, THREADS + fetch_threads, smem, stream>>>(kp);
   } else {
     grid &= ~1;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(THREADS);
+    cfg.blockDim = dim3(THREADS + fetch_threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -1132,6 +1239,7 @@ int conv_gemm_launch(const ConvGemmDesc& d_in, cudaStream_t stream) {
     d.block_n = 256;
   }
   VB_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "conv_gemm: empty problem M=%d N=%d K=%d", d.M, d.N, d.K);
+  d.res_slots = use_res_fetch(d) ? 3 : 0;          // (tile-width decisions below account for a 3-slot ring)
   const bool batched = d.kchunk > 0;               // batched split-K GEMM (weight gradients)
   VB_REQUIRE(batched || d.K % BK == 0, "conv_gemm: K=%d must be a multiple of %d", d.K, BK);
   if (batched) {
@@ -1336,6 +1444,20 @@ int conv_gemm_launch(const ConvGemmDesc& d_in, cudaStream_t stream) {
   // ---- shared-memory budget: A ring + B ring ----
   const size_t a_stage = (size_t)kp.a_plane_bytes * planes;
   const size_t b_stage = (size_t)(bn / cg) * 128 * planes;
+  if (d.res_slots > 0) {
+    if (ew != 2) {
+      d.res_slots = 0;                               // (e.g. forced single set): row owners load the residual themselves
+    } else {
+      // a fourth slot when it fits next to the minimum operand configuration, else make sure three do
+      const size_t need = (kp.num_n_blocks == 1 && ((kp.num_m_blocks + cg - 1) / cg >= 2 * (num_sms() / cg)))
+                              ? (size_t)kp.a_chunks * kp.b_per_a * b_stage + 2 * a_stage : 2 * (a_stage + b_stage);
+      d.res_slots = 4;
+      while (d.res_slots >= 2 && fixed_smem(bn, d) + need > SMEM_BUDGET) --d.res_slots;
+      if (d.res_slots < 2) d.res_slots = 0;
+    }
+  }
+  kp.res_fetch = d.res_slots > 0 ? 1 : 0;
+  kp.res_slots = d.res_slots;
   kp.staging_bufs = staging_tiles(d);
   kp.staging_total = (uint32_t)staging_bytes(d);
   const size_t avail = SMEM_BUDGET - fixed_smem(bn, d);

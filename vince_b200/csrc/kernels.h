@@ -58,6 +58,7 @@ struct ConvGemmDesc {
   int kchunk;                 // K elements per split (multiple of 64)
   int taps;                   // 1 or 9
   int shift_w;
+  int res_slots;              // internal (set by conv_gemm_launch): residual tiles of the apply epilogue's cp.async ring
 };
 int conv_gemm_launch(const ConvGemmDesc& d, cudaStream_t stream);
 // eval-mode BatchNorm: coef[2][C] = (gamma / sqrt(running_var + eps), beta - running_mean * scale)
