@@ -86,8 +86,9 @@ def ncu_conv_traffic(cfg):
             rows = list(csv.reader(open(path, newline="")))
             hdr = rows[0]
             k, r, w = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[rows[1][r]]
-            vals = [(float(x[r].replace(",", "")) + float(x[w].replace(",", ""))) * unit for x in rows[2:] if "conv_gemm" in x[k]]
+            units = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            ur, uw = units[rows[1][r]], units[rows[1][w]]             # (ncu picks a unit per column)
+            vals = [float(x[r].replace(",", "")) * ur + float(x[w].replace(",", "")) * uw for x in rows[2:] if "conv_gemm" in x[k]]
             if vals:
                 return round(sum(vals) / len(vals)), len(vals), name
         except Exception:
