@@ -15,12 +15,14 @@
 // fp32 value is carried as a fp16 (hi, lo) pair and each k-step issues three MMAs lo*hi + hi*lo + hi*hi into the same
 // accumulator ("fp16x3", passes = 3).  passes = 1 is plain fp16.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (separate A and B rings), warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store; per-channel sum / sum-of-squares for
-// train-mode BatchNorm accumulated in fp64; the LAST CTA to finish turns the sums into per-channel scale/shift and
-// updates the running statistics, so no separate BN-finalize launch exists).  Accumulators are double-buffered in
-// TMEM so the epilogue of tile t overlaps the main loop of tile t+1.  One CTA per SM; tiles are handed out round-robin
-// with the M index fastest so that concurrently running CTAs share the weight tile through L2.
+// Warp roles: warps 0..3 = TMA producers (activation hi / lo planes, weight hi / lo planes), warp 4 = TMEM allocator + MMA
+// issuer, then one or two SETS of four epilogue warps (one warp per TMEM lane quarter; TMEM -> registers -> swizzled smem
+// -> TMA store; per-channel sum / sum-of-squares for train-mode BatchNorm accumulated in double-float / fp64; the LAST CTA
+// to finish turns the sums into per-channel scale/shift and updates the running statistics, so no separate BN-finalize
+// launch exists), and - apply epilogue with a residual on the small-K GEMMs only - two residual fetcher warps.
+// 288 / 416 / 480 threads.  Accumulators are double-buffered in TMEM so the epilogue of tile t overlaps the main loop of
+// tile t+1.  One CTA per SM; tiles are handed out round-robin with the M index fastest so that concurrently running CTAs
+// share the weight tile through L2.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -43,8 +45,8 @@ struct GemmKernelParams {
   CUtensorMap out_hi, out_lo;    // EPI == 1: fp16 (hi, lo) output planes (box 32 channels x 128 rows, SWIZZLE_64B)
   int res_fetch;                 // EPI == 1: residual tiles are fetched by two extra warps (cp.async) into a ring of
   int res_slots;                 // res_slots 16 KB tiles behind the output staging tiles (0: row owners load registers)
-  int staging_bufs;              // output staging tiles in shared memory (1 or 2)
-  uint32_t staging_total;        // bytes of the staging area: staging_bufs output tiles (+ 2 residual tiles, EPI == 1)
+  int staging_bufs;              // output staging tiles in shared memory (1, 2 or 4)
+  uint32_t staging_total;        // bytes of the staging area: staging_bufs output tiles + res_slots residual tiles
   // EPI == 1 ("apply" epilogue): out = relu?( acc*alpha*coef[c] + coef[N+c] + residual ) split into fp16 planes
   const float* ep_coef;          // [2][N] per-channel (scale, shift): BatchNorm coefficients
   int res_kind;                  // 0 none, 1 fp16 planes [M,N], 2 bn(res_raw) with res_coef (downsample branch)
@@ -1094,9 +1096,9 @@ static int num_sms() {
   return sms[dev];
 }
 
-// Output staging tiles: two (one barrier per chunk instead of two) when a tile has few k-blocks, i.e. when the layer is
-// bound by its epilogue and shared memory is not needed for a deep operand ring; plus two residual tiles for the apply
-// epilogue with a residual.
+// Output staging tiles: two (one per epilogue set) when a tile has at most 8 k-blocks, i.e. when the layer is bound by
+// its epilogue and shared memory is not needed for a deep operand ring; four (two per set: one barrier per chunk instead
+// of two) for plain GEMMs of one or two k-blocks; behind them the residual ring of the fetcher warps, when used.
 // Apply epilogue with a residual on the small-K plain GEMMs (the two-pass route's recompute pass): the residual tiles are
 // fetched by two extra warps into a shared-memory ring (see the kernel); needs the two epilogue sets' configuration
 static bool use_res_fetch(const ConvGemmDesc& d) {
