@@ -706,7 +706,10 @@ class VinceQueueModel(BaseModel):
         key = tuple(p.data_ptr() for p in dst) + tuple(p.data_ptr() for p in src)
         every = [(p, p.data_ptr()) for p in dst + src]
         step = max(1, len(every) // 16)
-        self._ema_probe = (encoder_model, every, every[::step] + every[-1:], _PARAM_EPOCH[0])
+        # the storages are kept alive with the table: if a tensor is swapped out behind the probe's back (p.data = ...), the
+        # kernel keeps writing into memory that is still allocated until the next full check rebuilds the table
+        self._ema_probe = (encoder_model, every, every[::step] + every[-1:], _PARAM_EPOCH[0],
+                           [p.untyped_storage() for p in dst + src])
         if self._ema_key != key:
             chunks = []
             for d, s in zip(dst, src):
