@@ -81,15 +81,30 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a, double*
   const float4 is = __ldg(reinterpret_cast<const float4*>(a.coef + 3 * a.C + c));
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   float mx = 0.f;
-  for (int64_t m = (int64_t)blockIdx.x * rp + lrow; m < a.M; m += (int64_t)gridDim.x * rp) {
-    const float4 raw = __ldg(reinterpret_cast<const float4*>(a.raw + m * a.C + c));
-    const float4 d = bwd_dz4(a, m, c, raw, sc, sh);
+  // two rows per trip: both rows' loads (raw, dA, dB / mask planes) are issued before either is consumed - twice the bytes
+  // in flight per thread (this pass ran at half the HBM rate of the apply pass) - and accumulated in row order, so the sums
+  // are bit-identical to the one-row loop
+  const int64_t stride = (int64_t)gridDim.x * rp;
+  auto acc = [&](const float4& raw, const float4& d) {
     s1[0] += d.x, s1[1] += d.y, s1[2] += d.z, s1[3] += d.w;
     s2[0] = fmaf(d.x, (raw.x - mu.x) * is.x, s2[0]);
     s2[1] = fmaf(d.y, (raw.y - mu.y) * is.y, s2[1]);
     s2[2] = fmaf(d.z, (raw.z - mu.z) * is.z, s2[2]);
     s2[3] = fmaf(d.w, (raw.w - mu.w) * is.w, s2[3]);
     mx = fmaxf(mx, fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w))));
+  };
+  int64_t m = (int64_t)blockIdx.x * rp + lrow;
+  for (; m + stride < a.M; m += 2 * stride) {
+    const float4 raw0 = __ldg(reinterpret_cast<const float4*>(a.raw + m * a.C + c));
+    const float4 raw1 = __ldg(reinterpret_cast<const float4*>(a.raw + (m + stride) * a.C + c));
+    const float4 d0 = bwd_dz4(a, m, c, raw0, sc, sh);
+    const float4 d1 = bwd_dz4(a, m + stride, c, raw1, sc, sh);
+    acc(raw0, d0);
+    acc(raw1, d1);
+  }
+  if (m < a.M) {
+    const float4 raw = __ldg(reinterpret_cast<const float4*>(a.raw + m * a.C + c));
+    acc(raw, bwd_dz4(a, m, c, raw, sc, sh));
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) red[0][threadIdx.x][i] = s1[i], red[1][threadIdx.x][i] = s2[i];
