@@ -515,7 +515,9 @@ def run_ours(a):
     cpu = cpu_baseline(wl, seconds=20.0) if world == 1 else {
         "value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "reference",
         "sample": "not measured at N>1 (see the N=1 line of the same run, or --impl reference)"}
-    ref_gpu = reference_same_gpu(wl, dev) if (world == 1 and not a.no_ref_gpu) else None
+    # context leg, opt-in (--ref-gpu): it runs the reference's PyTorch-eager + cuDNN path in this process, and the default
+    # bench process should launch nothing but this repo's kernels; the committed bench lines under profiles/ carry it
+    ref_gpu = reference_same_gpu(wl, dev) if (world == 1 and a.ref_gpu and not a.no_ref_gpu) else None
     wire = {"uint8": "uint8 HWC raw frames (the dataset workers' format), ToTensor+Normalize fused into the stem packing",
             "fp32": "fp32 NCHW normalised frames (the reference's post-transform wire format)"}
     line = {
@@ -804,7 +806,9 @@ def main():
                     help="uint8 = raw HWC frames, normalisation fused into the stem packing (default: the format the "
                          "reference's workers hold); fp32 = the reference's normalised NCHW tensors")
     ap.add_argument("--no-train", action="store_true", help="skip the extra full-training-step leg")
-    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the extra reference-on-this-GPU context leg")
+    ap.add_argument("--ref-gpu", action="store_true",
+                    help="also time the unmodified reference (PyTorch eager + cuDNN) on this GPU, for context")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="(default; kept for older scripts)")
     ap.add_argument("--profile-train", action="store_true", help="one full training step between profiler start/stop (ncu)")
     ap.add_argument("--profile-only", action="store_true",
                     help="stop after the device-resident timed steps (for runs under ncu; prints no bench value)")

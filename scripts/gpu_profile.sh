@@ -7,7 +7,7 @@ mkdir -p gpurun_out; rm -f gpurun_out/*.ncu-rep
 echo "== pytest -m gpu"; timeout 1800 python -m pytest tests -m gpu -q -s 2>&1 | grep -E "rel-L2|oracle|passed|failed|rror|kNN|gradients|losses|cfg|FAILED|skipped|halves|solver|SGD steps|saturation|stats_only|transposed" | tee gpurun_out/r02_pytest_gpu.log | tail -40
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/r02_smoke.log
 for c in 2 1 4; do
-echo "== bench --config $c"; timeout 900 python bench.py --config $c --steps 20 --warmup 5 2> gpurun_out/bench_cfg$c.err > gpurun_out/r02_bench_line_cfg$c.json
+echo "== bench --config $c"; timeout 900 python bench.py --config $c --steps 20 --warmup 5 --ref-gpu 2> gpurun_out/bench_cfg$c.err > gpurun_out/r02_bench_line_cfg$c.json
 python -c "
 import json
 d=json.load(open('gpurun_out/r02_bench_line_cfg$c.json')); t=d['train_step'] or {}
