@@ -170,3 +170,49 @@ def test_activation_arena_reuses_buffers():
     assert t2.data_ptr() == t1.data_ptr() and a.total == 1000 * 64 * 4
     t3 = a.alloc((10,), torch.float32)
     assert t3.data_ptr() != t2.data_ptr()
+
+
+def test_two_pass_policy_picks_the_wide_small_k_expansions():
+    """encoder.EncoderRunner._two_pass (host logic, no GPU): with the default policy the train-mode two-pass BatchNorm route
+    (transposed statistics pass + apply epilogue) is taken by exactly the Bottleneck 1x1 expansions of the 56x56 and 28x28
+    stages (K = 64 / 128, N = 4K: 7 of ResNet-50's 16), with VINCE_B200_TWOPASS=2 by all 16, never by a 3x3, a strided or a
+    reducing convolution, and never in ResNet-18 (BasicBlocks have no 1x1 expansion)."""
+    import vince_b200
+    for backbone, expect1, expect2 in (("ResNet50", 7, 16), ("ResNet18", 0, 0)):
+        args = make_args(backbone=backbone, batch_size=8, num_frames=2, queue_size=64, embedding_size=128, device="cpu")
+        runner = vince_b200.VinceModel(args).feature_extractor.module.runner
+        mains = [s for blk in runner.blocks for s in blk["convs"]]
+        picked = {}
+        for mode in (0, 1, 2):
+            runner.two_pass = mode
+            picked[mode] = [s for s in mains if runner._two_pass(s)]
+        assert len(picked[0]) == 0 and len(picked[1]) == expect1 and len(picked[2]) == expect2
+        for s in picked[2]:
+            assert s.R == 1 and s.stride == 1 and s.Cout == 4 * s.K
+        assert all(s.K <= 128 for s in picked[1])
+        downs = [blk["down"] for blk in runner.blocks if blk["down"] is not None]
+        runner.two_pass = 2
+        assert len(downs) == (4 if backbone == "ResNet50" else 3)        # (downsample branches keep the raw route: encoder.py)
+
+
+def test_graph_replay_runs_eagerly_when_disabled_or_profiled():
+    """ops.GraphReplay (host logic, no GPU): with graphs disabled (VINCE_B200_GRAPH=0) or while bench.py collects
+    per-launch events (ops.PROFILE) the launch list runs eagerly, `pre` first, in order, every call."""
+    from vince_b200 import ops
+    log = []
+    rep = ops.GraphReplay([lambda: log.append("a"), lambda: log.append("b")], pre=lambda: log.append("pre"))
+    saved_enabled, saved_profile = ops.GraphReplay.enabled, ops.PROFILE
+    try:
+        ops.GraphReplay.enabled = False
+        rep()
+        rep()
+        assert log == ["pre", "a", "b"] * 2 and rep.graph is None
+        ops.GraphReplay.enabled = True
+        ops.PROFILE = []
+        rep()
+        assert log == ["pre", "a", "b"] * 3 and rep.graph is None and rep.calls == 0
+    finally:
+        ops.GraphReplay.enabled, ops.PROFILE = saved_enabled, saved_profile
+    empty = ops.GraphReplay([])
+    empty()
+    assert empty.graph is None
