@@ -53,6 +53,33 @@ def main():
     a = ap.parse_args()
     dev = "cuda"
     B = a.batch
+    if not a.filter or a.filter in "stem 7x7/2":
+        # the stem runs over the packed overlapping-window layout (ops.stem_geometry): 224x224 frames -> 112x112x64
+        sg = ops.stem_geometry(224, 224)
+        M = B * sg["P"] * sg["Q"]
+        xs = [(torch.randn((B, sg["Ha"], sg["Wb"], 16), device=dev).to(torch.float16),
+               (torch.randn((B, sg["Ha"], sg["Wb"], 16), device=dev) * 0.01).to(torch.float16)) for _ in range(3)]
+        w_hi = (torch.randn((64, 256), device=dev) * 0.05).to(torch.float16)
+        w_lo = (torch.randn((64, 256), device=dev) * 0.0005).to(torch.float16)
+        outs = [torch.empty((M, 64), device=dev) for _ in range(3)]
+        stats = torch.zeros((128,), device=dev, dtype=torch.float64)
+        runs = [ops.build_conv_fwd(xs[i][0], xs[i][1], w_hi, w_lo, outs[i], M, 64, 256, passes=3,
+                                   geom=dict(sg["geom"], batch=B), stats=None if a.nostats else stats) for i in range(3)]
+        for r in runs:
+            r()
+        torch.cuda.synchronize()
+        times = []
+        for it in range(a.iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            runs[it % 3]()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) * 1e3)
+        t = sorted(times)[len(times) // 2]
+        print("%-28s M=%8d N=%4d K=%5d  %8.1f us  %7.1f TFLOP/s (alg)  min %.1f us" % ("stem 7x7/2 (packed K=256)", M, 64, 147,
+              t, 2.0 * M * 64 * 147 / t / 1e6, min(times)), flush=True)
+        del xs, outs
     for name, H, W, Cin, Cout, R, stride, pad in SHAPES:
         if a.filter and a.filter not in name:
             continue

@@ -1112,6 +1112,9 @@ static bool use_res_fetch(const ConvGemmDesc& d) {
 static int staging_tiles(const ConvGemmDesc& d) {
   // one or two k-blocks per tile: two tiles for each of the two epilogue warp sets (one barrier per chunk)
   int nbuf = (d.K / BK <= 2 && !d.im2col) ? 4 : ((d.K / BK <= 8) ? 2 : 1);
+  // the stem (multi-tap im2col over the packed window layout, 4 k-blocks) is bound by its operand ring, not by the epilogue:
+  // one tile and one epilogue set leave room for one more im2col stage (B200: 440 -> 399 us at B = 256)
+  if (d.im2col && d.R * d.S > 1 && d.K / BK <= 8) nbuf = 1;
   if (d.res_slots > 0) nbuf = 2;                     // the residual ring takes the room of the second pair of tiles
   const char* e = getenv("VINCE_B200_STAGING");      // debug / A-B comparison: 1, 2 or 4
   if (e && (atoi(e) == 1 || atoi(e) == 2 || (atoi(e) == 4 && nbuf == 4))) nbuf = atoi(e);
