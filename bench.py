@@ -358,6 +358,15 @@ def run_ours(a):
     warm = max(a.warmup, 3)
     for _ in range(warm):
         hp.step(data, queue_data)
+    torch.cuda.synchronize()
+    # the W warm-up steps build the plans and capture the graphs; short steps (ResNet-18: 7 ms) are then through them
+    # before the clocks / power management have settled, and the timed region read 5-8 % slow against every later leg:
+    # keep stepping (untimed, counted in "warmup") for another 0.5 s of steady work
+    t_warm = time.perf_counter()
+    while time.perf_counter() - t_warm < 0.5 and not a.profile_only:
+        hp.step(data, queue_data)
+        torch.cuda.synchronize()
+        warm += 1
     # ---- device-resident leg (value) with per-launch events on the tensor-core kernel ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
