@@ -852,7 +852,7 @@ def test_reference_solver_runs_unchanged_on_vince_b200_classes():
     worst = max(upd)
     print("after two SGD steps: all parameters + buffers rel-L2 %.2e vs the reference; worst per-tensor update error %.2e (%s)"
           % (glob, worst[0], worst[1]))
-    assert glob < 5e-4 and worst[0] < 1e-1
+    assert glob < 5e-4 and worst[0] < 2e-1          # (measured 1.2e-4 and 7.3e-2: BatchNorm gammas of a B = 8 step)
     for name in ("bn1.running_mean", "layer4.1.bn2.running_var"):
         k_ = "feature_extractor.module.model." + name
         assert rel(post[k_].cpu(), rpost[k_]) < 1e-3, name
